@@ -1,0 +1,82 @@
+// common.cuh -- shared declarations of the sm_100a kernels and their launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svc {
+
+constexpr int kMaxLevels = 8;
+constexpr int kNumSms = 148;  // B200
+
+// Device layout of one Y pyramid "slot" (one frame): levels are stored one
+// after another, each with a 128-byte-multiple row pitch (TMA needs 16-byte
+// strides; the reference keeps tightly packed Mats, libs/encoder.cpp:197-219,
+// the stateless entry points repack at the PCIe boundary).
+struct PyrLayout {
+  uint32_t levels;
+  uint32_t w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
+  uint64_t off[kMaxLevels];
+  uint64_t slot_bytes;  // multiple of 256
+};
+
+inline PyrLayout make_pyr_layout(uint32_t pw, uint32_t ph, uint32_t levels) {
+  PyrLayout L{};
+  L.levels = levels;
+  uint64_t off = 0;
+  for (uint32_t l = 0; l < levels; ++l) {
+    L.w[l] = pw >> l;
+    L.h[l] = ph >> l;
+    L.pitch[l] = (L.w[l] + 127u) & ~127u;
+    L.off[l] = off;
+    off += (uint64_t)L.pitch[l] * L.h[l];
+    off = (off + 255u) & ~(uint64_t)255u;
+  }
+  L.slot_bytes = off;
+  return L;
+}
+
+// ---- K1: zero pad + BGR -> Y (level 0) and pyrDown (levels 1..) -------------
+// frames: n x (h*w*3) interleaved BGR; slot s of the pyramid array receives
+// frame s - first_slot.
+cudaError_t launch_bgr_to_y(const uint8_t* d_bgr, uint32_t w, uint32_t h,
+                            uint8_t* d_pyr, const PyrLayout& lay,
+                            uint32_t first_slot, uint32_t n_frames,
+                            cudaStream_t st);
+cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
+                            uint32_t src_level, uint32_t first_slot,
+                            uint32_t n_frames, cudaStream_t st);
+
+// ---- K2: hierarchical block matching ---------------------------------------
+struct HbmaParams {
+  const uint8_t* pyr;  // slot array; frame i: tracked = slot i, anchor = slot i+1
+  PyrLayout lay;
+  uint32_t bw, bh;  // base-level block size
+  uint32_t r;       // search_range / 2^(levels-1), used at every level
+  uint32_t mvw, mvh;
+  float2* mv;   // n_frames x mvh x mvw, may be null
+  float* mad;   // n_frames x mvh x mvw, may be null
+  uint32_t n_frames;
+};
+cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches);
+
+// ---- K3: block DCT + stream layout -------------------------------------------
+struct DctParams {
+  const uint8_t* bgr;  // n x (h*w*3)
+  uint32_t w, h, pw, ph;
+  uint32_t tbw, tbh;
+  uint32_t n_frames;
+  // planar output: 3 planes per frame, each ph x pw floats
+  float* planes;          // n x 3 x ph x pw (may be null)
+  // stream output
+  uint8_t* stream;        // n x frame_stream_bytes (may be null)
+  uint64_t frame_stream_bytes;
+  const uint32_t* block_types;  // n x mvw*mvh or null
+  uint32_t mv_block_w, mv_block_h, mv_field_w, mv_field_h;
+  float* scratch_planes;  // >= min(n, scratch_frames) x 3 x ph x pw, for the generic path
+  uint32_t scratch_frames;
+};
+cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* n_launches);
+// once per device (opt-in shared memory sizes etc.)
+cudaError_t prepare_dct_kernels();
+
+}  // namespace svc

@@ -1,0 +1,756 @@
+// svc_api.cu -- the C ABI of libsvc_b200.so (include/svc_b200.h): argument
+// validation, device memory/stream management and the launch sequence of the
+// three hot-path kernels.  No CPU implementation of any stage exists here: a
+// missing device or a CUDA failure is reported, never worked around.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#pragma GCC visibility push(default)
+#include "../../include/svc_b200.h"
+#pragma GCC visibility pop
+#include "common.cuh"
+
+using namespace svc;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_device = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  cudaGetLastError();  // clear sticky-less errors
+  return SVC_ERR_CUDA;
+}
+
+#define CU(call)                                       \
+  do {                                                 \
+    cudaError_t e__ = (call);                          \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+bool g_prepared[64] = {};
+
+int prepare_device(int dev) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (dev < 0 || dev >= n) return fail(SVC_ERR_CUDA, "no such CUDA device: " + std::to_string(dev));
+  CU(cudaSetDevice(dev));
+  if (dev < 64 && !g_prepared[dev]) {
+    CU(prepare_dct_kernels());
+    g_prepared[dev] = true;
+  }
+  return SVC_OK;
+}
+
+// Preconditions of EstimateMotionHierarchical (libs/motion.cpp:417-433) plus
+// the divisibility the reference silently assumes (block / 2^(L-1) != 0).
+int check_hbma_args(uint32_t levels, uint32_t fw, uint32_t fh, uint32_t range,
+                    uint32_t bw, uint32_t bh, bool allow_zero_range) {
+  if (levels < 1 || levels > SVC_MAX_LEVELS)
+    return fail(SVC_ERR_INVALID_ARG, "level_count must be in [1, 8]");
+  if (fw == 0 || fh == 0 || bw == 0 || bh == 0)
+    return fail(SVC_ERR_INVALID_ARG, "frame and block dimensions must be > 0");
+  if (fw % bw || fh % bh)
+    return fail(SVC_ERR_INVALID_ARG, "frame dimensions must be divisible by the block dimensions");
+  const uint32_t red = 1u << (levels - 1);
+  if (bw % red || bh % red)
+    return fail(SVC_ERR_INVALID_ARG, "block dimensions must be divisible by 2^(level_count-1)");
+  if (!allow_zero_range && range < red)
+    return fail(SVC_ERR_INVALID_ARG, "search_range must be >= 2^(level_count-1)");
+  if (bw > 128 || bh > 128)
+    return fail(SVC_ERR_UNSUPPORTED, "block dimensions above 128 are not supported");
+  if (fw > 32768 || fh > 32768)
+    return fail(SVC_ERR_UNSUPPORTED, "frame dimensions above 32768 are not supported");
+  if (range > 4096) return fail(SVC_ERR_UNSUPPORTED, "search_range above 4096 is not supported");
+  return SVC_OK;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+  template <class T>
+  T* as() { return static_cast<T*>(p); }
+};
+
+constexpr size_t kSlack = 256;  // kernels may read one aligned word past a row
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+const char* svc_last_error(void) { return g_err.c_str(); }
+const char* svc_version(void) { return "svc_b200 0.1 (sm_100a)"; }
+
+int svc_device_count(int* count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  if (count) *count = n;
+  return SVC_OK;
+}
+
+int svc_set_device(int device) {
+  if (device < 0) return fail(SVC_ERR_INVALID_ARG, "device must be >= 0");
+  g_device = device;
+  return SVC_OK;
+}
+
+uint32_t svc_padded_dim(uint32_t a, uint32_t mv_block, uint32_t levels) {
+  if (mv_block == 0 || levels == 0 || levels > SVC_MAX_LEVELS) return 0;
+  const uint32_t l = std::lcm(mv_block, 1u << (levels - 1));
+  return (a + l - 1) / l * l;
+}
+
+uint64_t svc_serialized_frame_bytes(uint32_t w, uint32_t h, uint32_t tbw,
+                                    uint32_t tbh, uint32_t channels) {
+  if (!tbw || !tbh) return 0;
+  const uint64_t nx = (w + tbw - 1) / tbw, ny = (h + tbh - 1) / tbh;
+  return nx * ny * (4 + (uint64_t)channels * tbw * tbh * 4);
+}
+
+int svc_write_header(uint32_t n_input_frames, uint32_t frame_w, uint32_t frame_h,
+                     uint32_t padded_w, uint32_t padded_h, uint32_t tbw,
+                     uint32_t tbh, uint32_t channels, uint8_t out32[32]) {
+  if (!out32) return fail(SVC_ERR_INVALID_ARG, "out32 is null");
+  if (padded_w < frame_w || padded_h < frame_h)
+    return fail(SVC_ERR_INVALID_ARG, "padded dimensions smaller than the frame");
+  const uint32_t hdr[8] = {n_input_frames ? n_input_frames - 1 : 0, frame_w, frame_h,
+                           padded_w - frame_w, padded_h - frame_h, tbw, tbh, channels};
+  memcpy(out32, hdr, 32);
+  return SVC_OK;
+}
+
+int svc_patch_block_types(uint8_t* frame_stream, uint32_t frame_w, uint32_t frame_h,
+                          uint32_t tbw, uint32_t tbh, uint32_t channels,
+                          uint32_t mv_block_w, uint32_t mv_block_h,
+                          uint32_t mv_field_w, const uint32_t* block_types) {
+  if (!frame_stream || !block_types) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  if (!tbw || !tbh || !mv_block_w || !mv_block_h) return fail(SVC_ERR_INVALID_ARG, "zero block size");
+  const size_t rec = 4 + (size_t)channels * tbw * tbh * 4;
+  uint8_t* p = frame_stream;
+  for (uint32_t y = 0; y < frame_h; y += tbh)
+    for (uint32_t x = 0; x < frame_w; x += tbw, p += rec)
+      memcpy(p, &block_types[(y / mv_block_h) * mv_field_w + x / mv_block_w], 4);
+  return SVC_OK;
+}
+
+// ---- stateless drop-ins ---------------------------------------------------------
+
+static int hbma_host(const uint8_t* const* tracked, const uint8_t* const* anchor,
+                     uint32_t levels, uint32_t fw, uint32_t fh, uint32_t range,
+                     uint32_t bw, uint32_t bh, float* mv, float* mad, bool ebma) {
+  if (!tracked || !anchor || !mv || !mad) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  for (uint32_t l = 0; l < levels && l < SVC_MAX_LEVELS; ++l)
+    if (!tracked[l] || !anchor[l]) return fail(SVC_ERR_INVALID_ARG, "null pyramid level");
+  int rc = check_hbma_args(levels, fw, fh, range, bw, bh, ebma);
+  if (rc) return rc;
+  rc = prepare_device(g_device);
+  if (rc) return rc;
+  const PyrLayout lay = make_pyr_layout(fw, fh, levels);
+  const uint32_t mvw = fw / bw, mvh = fh / bh;
+  DevBuf pyr, dmv, dmad;
+  CU(pyr.alloc(2 * lay.slot_bytes + kSlack));
+  CU(dmv.alloc(sizeof(float2) * mvw * mvh));
+  CU(dmad.alloc(sizeof(float) * mvw * mvh));
+  cudaStream_t st = 0;
+  for (uint32_t l = 0; l < levels; ++l) {
+    CU(cudaMemcpy2DAsync(pyr.as<uint8_t>() + lay.off[l], lay.pitch[l], tracked[l], lay.w[l],
+                         lay.w[l], lay.h[l], cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpy2DAsync(pyr.as<uint8_t>() + lay.slot_bytes + lay.off[l], lay.pitch[l], anchor[l],
+                         lay.w[l], lay.w[l], lay.h[l], cudaMemcpyHostToDevice, st));
+  }
+  HbmaParams p{};
+  p.pyr = pyr.as<uint8_t>();
+  p.lay = lay;
+  p.bw = bw;
+  p.bh = bh;
+  p.r = range >> (levels - 1);
+  p.mvw = mvw;
+  p.mvh = mvh;
+  p.mv = dmv.as<float2>();
+  p.mad = dmad.as<float>();
+  p.n_frames = 1;
+  CU(launch_hbma(p, st, nullptr));
+  CU(cudaMemcpyAsync(mv, dmv.p, sizeof(float2) * mvw * mvh, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(mad, dmad.p, sizeof(float) * mvw * mvh, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SVC_OK;
+}
+
+int svc_estimate_motion_hierarchical(const uint8_t* const* tracked_pyr,
+                                     const uint8_t* const* anchor_pyr,
+                                     uint32_t level_count, uint32_t frame_w,
+                                     uint32_t frame_h, uint32_t search_range,
+                                     uint32_t block_w, uint32_t block_h,
+                                     float* motion_field_xy, float* min_mad) {
+  return hbma_host(tracked_pyr, anchor_pyr, level_count, frame_w, frame_h, search_range,
+                   block_w, block_h, motion_field_xy, min_mad, false);
+}
+
+int svc_estimate_motion_hierarchical_16x16(const uint8_t* const* tracked_pyr,
+                                           const uint8_t* const* anchor_pyr,
+                                           uint32_t frame_w, uint32_t frame_h,
+                                           uint32_t search_range, float* mv_field_xy,
+                                           float* min_mad) {
+  return hbma_host(tracked_pyr, anchor_pyr, 4, frame_w, frame_h, search_range, 16, 16,
+                   mv_field_xy, min_mad, false);
+}
+
+int svc_estimate_motion_exhaustive(const uint8_t* tracked_frame, const uint8_t* anchor_frame,
+                                   uint32_t frame_w, uint32_t frame_h, uint32_t search_range,
+                                   uint32_t block_w, uint32_t block_h,
+                                   float* motion_field_xy, float* min_mad) {
+  const uint8_t* t[1] = {tracked_frame};
+  const uint8_t* a[1] = {anchor_frame};
+  return hbma_host(t, a, 1, frame_w, frame_h, search_range, block_w, block_h,
+                   motion_field_xy, min_mad, true);
+}
+
+int svc_y_pyramid(const uint8_t* bgr, uint32_t frame_w, uint32_t frame_h, uint32_t padded_w,
+                  uint32_t padded_h, uint32_t level_count, uint8_t* const* out_levels) {
+  if (!bgr || !out_levels) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  if (level_count < 1 || level_count > SVC_MAX_LEVELS)
+    return fail(SVC_ERR_INVALID_ARG, "level_count must be in [1, 8]");
+  for (uint32_t l = 0; l < level_count; ++l)
+    if (!out_levels[l]) return fail(SVC_ERR_INVALID_ARG, "null output level");
+  if (!frame_w || !frame_h || padded_w < frame_w || padded_h < frame_h)
+    return fail(SVC_ERR_INVALID_ARG, "bad frame / padded dimensions");
+  const uint32_t red = 1u << (level_count - 1);
+  if (padded_w % red || padded_h % red)
+    return fail(SVC_ERR_INVALID_ARG, "padded dimensions must be divisible by 2^(level_count-1)");
+  if (padded_w > 32768 || padded_h > 32768) return fail(SVC_ERR_UNSUPPORTED, "frame too large");
+  int rc = prepare_device(g_device);
+  if (rc) return rc;
+  const PyrLayout lay = make_pyr_layout(padded_w, padded_h, level_count);
+  DevBuf in, pyr;
+  const size_t in_bytes = (size_t)frame_w * frame_h * 3;
+  CU(in.alloc(in_bytes));
+  CU(pyr.alloc(lay.slot_bytes + kSlack));
+  cudaStream_t st = 0;
+  CU(cudaMemcpyAsync(in.p, bgr, in_bytes, cudaMemcpyHostToDevice, st));
+  CU(launch_bgr_to_y(in.as<uint8_t>(), frame_w, frame_h, pyr.as<uint8_t>(), lay, 0, 1, st));
+  for (uint32_t l = 0; l + 1 < level_count; ++l) CU(launch_pyr_down(pyr.as<uint8_t>(), lay, l, 0, 1, st));
+  for (uint32_t l = 0; l < level_count; ++l)
+    CU(cudaMemcpy2DAsync(out_levels[l], lay.w[l], pyr.as<uint8_t>() + lay.off[l], lay.pitch[l],
+                         lay.w[l], lay.h[l], cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SVC_OK;
+}
+
+static int check_dct_args(uint32_t w, uint32_t h, uint32_t pw, uint32_t ph, uint32_t tbw, uint32_t tbh) {
+  if (!w || !h || pw < w || ph < h) return fail(SVC_ERR_INVALID_ARG, "bad frame / padded dimensions");
+  if (!tbw || !tbh) return fail(SVC_ERR_INVALID_ARG, "transform block dimensions must be > 0");
+  if (pw % tbw || ph % tbh)
+    return fail(SVC_ERR_INVALID_ARG, "padded dimensions must be divisible by the transform block");
+  if (tbw > 32 || tbh > 32) return fail(SVC_ERR_UNSUPPORTED, "transform blocks above 32x32 are not supported");
+  if (pw > 32768 || ph > 32768) return fail(SVC_ERR_UNSUPPORTED, "frame too large");
+  return SVC_OK;
+}
+
+int svc_dct_planar(const uint8_t* bgr, uint32_t frame_w, uint32_t frame_h, uint32_t padded_w,
+                   uint32_t padded_h, uint32_t tbw, uint32_t tbh, float* const* planes) {
+  if (!bgr || !planes || !planes[0] || !planes[1] || !planes[2])
+    return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  int rc = check_dct_args(frame_w, frame_h, padded_w, padded_h, tbw, tbh);
+  if (rc) return rc;
+  rc = prepare_device(g_device);
+  if (rc) return rc;
+  const size_t in_bytes = (size_t)frame_w * frame_h * 3;
+  const size_t plane_elems = (size_t)padded_w * padded_h;
+  DevBuf in, out, tmp;
+  CU(in.alloc(in_bytes));
+  CU(out.alloc(plane_elems * 3 * sizeof(float)));
+  CU(tmp.alloc(plane_elems * 3 * sizeof(float)));
+  cudaStream_t st = 0;
+  CU(cudaMemcpyAsync(in.p, bgr, in_bytes, cudaMemcpyHostToDevice, st));
+  DctParams p{};
+  p.bgr = in.as<uint8_t>();
+  p.w = frame_w; p.h = frame_h; p.pw = padded_w; p.ph = padded_h;
+  p.tbw = tbw; p.tbh = tbh;
+  p.n_frames = 1;
+  p.planes = out.as<float>();
+  p.scratch_planes = tmp.as<float>();
+  p.scratch_frames = 1;
+  CU(launch_dct(p, st, nullptr));
+  for (int c = 0; c < 3; ++c)
+    CU(cudaMemcpyAsync(planes[c], out.as<float>() + c * plane_elems, plane_elems * sizeof(float),
+                       cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SVC_OK;
+}
+
+int svc_encode_frame_stream(const uint8_t* bgr, uint32_t frame_w, uint32_t frame_h,
+                            uint32_t padded_w, uint32_t padded_h, uint32_t tbw, uint32_t tbh,
+                            uint32_t mv_block_w, uint32_t mv_block_h,
+                            const uint32_t* block_types, uint8_t* out) {
+  if (!bgr || !out) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  int rc = check_dct_args(frame_w, frame_h, padded_w, padded_h, tbw, tbh);
+  if (rc) return rc;
+  if (!mv_block_w || !mv_block_h || padded_w % mv_block_w || padded_h % mv_block_h)
+    return fail(SVC_ERR_INVALID_ARG, "padded dimensions must be divisible by the mv block");
+  rc = prepare_device(g_device);
+  if (rc) return rc;
+  const size_t in_bytes = (size_t)frame_w * frame_h * 3;
+  const size_t plane_elems = (size_t)padded_w * padded_h;
+  const uint64_t sbytes = svc_serialized_frame_bytes(frame_w, frame_h, tbw, tbh, 3);
+  const uint32_t mvw = padded_w / mv_block_w, mvh = padded_h / mv_block_h;
+  DevBuf in, stream, scratch, bt;
+  CU(in.alloc(in_bytes));
+  CU(stream.alloc(sbytes));
+  CU(scratch.alloc(plane_elems * 6 * sizeof(float)));
+  cudaStream_t st = 0;
+  CU(cudaMemcpyAsync(in.p, bgr, in_bytes, cudaMemcpyHostToDevice, st));
+  if (block_types) {
+    CU(bt.alloc(sizeof(uint32_t) * mvw * mvh));
+    CU(cudaMemcpyAsync(bt.p, block_types, sizeof(uint32_t) * mvw * mvh, cudaMemcpyHostToDevice, st));
+  }
+  DctParams p{};
+  p.bgr = in.as<uint8_t>();
+  p.w = frame_w; p.h = frame_h; p.pw = padded_w; p.ph = padded_h;
+  p.tbw = tbw; p.tbh = tbh;
+  p.n_frames = 1;
+  p.stream = stream.as<uint8_t>();
+  p.frame_stream_bytes = sbytes;
+  p.block_types = block_types ? bt.as<uint32_t>() : nullptr;
+  p.mv_block_w = mv_block_w; p.mv_block_h = mv_block_h;
+  p.mv_field_w = mvw; p.mv_field_h = mvh;
+  p.scratch_planes = scratch.as<float>();
+  p.scratch_frames = 1;
+  CU(launch_dct(p, st, nullptr));
+  CU(cudaMemcpyAsync(out, stream.p, sbytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SVC_OK;
+}
+
+// ---- memory helpers -------------------------------------------------------------
+
+void* svc_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void svc_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+void* svc_device_alloc(int device, size_t bytes) {
+  void* p = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void svc_device_free(int device, void* p) {
+  if (p && cudaSetDevice(device) == cudaSuccess) cudaFree(p);
+}
+int svc_memcpy_h2d(int device, void* dst, const void* src, size_t bytes) {
+  CU(cudaSetDevice(device));
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return SVC_OK;
+}
+int svc_memcpy_d2h(int device, void* dst, const void* src, size_t bytes) {
+  CU(cudaSetDevice(device));
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return SVC_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================
+// Session
+// =============================================================================
+struct svc_session {
+  svc_session_config cfg{};
+  svc_session_info info{};
+  PyrLayout lay{};
+  int device = 0;
+  cudaStream_t stream = nullptr;  // compute
+  bool own_stream = false;
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // host path copy streams
+  uint8_t* d_pyr = nullptr;  // max_batch + 1 slots
+  bool have_prev = false;
+  float* d_scratch = nullptr;  // generic DCT path only
+  uint32_t scratch_frames = 0;
+  // host path staging (double buffered), allocated on first use
+  uint8_t* d_in[2] = {nullptr, nullptr};
+  float* d_mv[2] = {nullptr, nullptr};
+  float* d_mad[2] = {nullptr, nullptr};
+  uint8_t* d_st[2] = {nullptr, nullptr};
+  uint32_t* d_bt[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
+  bool staging = false;
+  uint64_t launches = 0;
+};
+
+namespace {
+
+bool needs_scratch(const svc_session* s) {
+  return !(s->cfg.transform_block_w == 8 && s->cfg.transform_block_h == 8 &&
+           s->cfg.frame_w == s->info.padded_w);
+}
+
+// One batch (<= max_batch frames), everything on the device, async on s->stream.
+int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, float* d_mv,
+                        float* d_mad, uint8_t* d_stream, const uint32_t* d_bt,
+                        uint32_t* n_enc_out) {
+  const uint32_t first_slot = s->have_prev ? 1u : 0u;
+  const uint32_t n_enc = s->have_prev ? m : m - 1;
+  const uint32_t mvn = s->info.mv_field_w * s->info.mv_field_h;
+  int nl = 0;
+  CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, s->d_pyr, s->lay, first_slot, m, s->stream));
+  nl += 1;
+  for (uint32_t l = 0; l + 1 < s->lay.levels; ++l) {
+    CU(launch_pyr_down(s->d_pyr, s->lay, l, first_slot, m, s->stream));
+    nl += 1;
+  }
+  if (n_enc && (d_mv || d_mad)) {
+    HbmaParams p{};
+    p.pyr = s->d_pyr;
+    p.lay = s->lay;
+    p.bw = s->cfg.mv_block_w;
+    p.bh = s->cfg.mv_block_h;
+    p.r = s->cfg.mv_search_range >> (s->cfg.pyr_lvl_count - 1);
+    p.mvw = s->info.mv_field_w;
+    p.mvh = s->info.mv_field_h;
+    p.mv = reinterpret_cast<float2*>(d_mv);
+    p.mad = d_mad;
+    p.n_frames = n_enc;
+    CU(launch_hbma(p, s->stream, &nl));
+  }
+  if (n_enc && d_stream) {
+    DctParams p{};
+    p.bgr = d_frames + (size_t)(m - n_enc) * s->info.frame_in_bytes;
+    p.w = s->cfg.frame_w; p.h = s->cfg.frame_h;
+    p.pw = s->info.padded_w; p.ph = s->info.padded_h;
+    p.tbw = s->cfg.transform_block_w; p.tbh = s->cfg.transform_block_h;
+    p.n_frames = n_enc;
+    p.stream = d_stream;
+    p.frame_stream_bytes = s->info.frame_stream_bytes;
+    p.block_types = d_bt;
+    p.mv_block_w = s->cfg.mv_block_w; p.mv_block_h = s->cfg.mv_block_h;
+    p.mv_field_w = s->info.mv_field_w; p.mv_field_h = s->info.mv_field_h;
+    p.scratch_planes = s->d_scratch;
+    p.scratch_frames = s->scratch_frames;
+    CU(launch_dct(p, s->stream, &nl));
+  }
+  // keep the last frame's pyramid as the next tracked frame (libs/encoder.cpp:661-663)
+  const uint32_t last = first_slot + m - 1;
+  if (last != 0) {
+    CU(cudaMemcpyAsync(s->d_pyr, s->d_pyr + (size_t)last * s->lay.slot_bytes, s->lay.slot_bytes,
+                       cudaMemcpyDeviceToDevice, s->stream));
+  }
+  s->have_prev = true;
+  s->launches += (uint64_t)nl;
+  (void)mvn;
+  if (n_enc_out) *n_enc_out = n_enc;
+  return SVC_OK;
+}
+
+int ensure_staging(svc_session* s) {
+  if (s->staging) return SVC_OK;
+  const size_t B = s->info.max_batch;
+  const size_t mvn = (size_t)s->info.mv_field_w * s->info.mv_field_h;
+  CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CU(cudaMalloc(&s->d_in[b], B * s->info.frame_in_bytes));
+    CU(cudaMalloc(&s->d_mv[b], B * mvn * sizeof(float2)));
+    CU(cudaMalloc(&s->d_mad[b], B * mvn * sizeof(float)));
+    CU(cudaMalloc(&s->d_st[b], B * s->info.frame_stream_bytes));
+    CU(cudaMalloc(&s->d_bt[b], B * mvn * sizeof(uint32_t)));
+    CU(cudaEventCreateWithFlags(&s->ev_in[b], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s->ev_comp[b], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s->ev_out[b], cudaEventDisableTiming));
+  }
+  s->staging = true;
+  return SVC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int svc_session_create(const svc_session_config* cfg, svc_session** out) {
+  if (!cfg || !out) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  if (cfg->struct_size != sizeof(svc_session_config))
+    return fail(SVC_ERR_INVALID_ARG, "svc_session_config.struct_size mismatch");
+  *out = nullptr;
+  // Validate(EncoderConfig), libs/encoder.cpp:62-142 (hot-path fields)
+  if (cfg->mv_block_w < 1) return fail(SVC_ERR_INVALID_ARG, "invalid mv block width: must be > 0");
+  if (cfg->mv_block_h < 1) return fail(SVC_ERR_INVALID_ARG, "invalid mv block height: must be > 0");
+  if (cfg->pyr_lvl_count < 1) return fail(SVC_ERR_INVALID_ARG, "invalid pyramid level count: must be > 0");
+  if (cfg->pyr_lvl_count > SVC_MAX_LEVELS) return fail(SVC_ERR_UNSUPPORTED, "pyramid level count above 8");
+  const uint32_t red = 1u << (cfg->pyr_lvl_count - 1);
+  if (cfg->mv_search_range / red == 0)
+    return fail(SVC_ERR_INVALID_ARG,
+                "invalid mv search and pyramid level count: the quotient from dividing the mv "
+                "search range by the pyramid level reduction factor must be > 0");
+  if (cfg->transform_block_w < 1) return fail(SVC_ERR_INVALID_ARG, "invalid transform block width: must be > 0");
+  if (cfg->transform_block_h < 1) return fail(SVC_ERR_INVALID_ARG, "invalid transform block height: must be > 0");
+  if (cfg->transform_block_w > cfg->mv_block_w)
+    return fail(SVC_ERR_INVALID_ARG, "transform block width must be <= mv block width");
+  if (cfg->transform_block_h > cfg->mv_block_h)
+    return fail(SVC_ERR_INVALID_ARG, "transform block height must be <= mv block height");
+  if (cfg->mv_block_w % cfg->transform_block_w)
+    return fail(SVC_ERR_INVALID_ARG, "mv block width must be divisible by transform block width");
+  if (cfg->mv_block_h % cfg->transform_block_h)
+    return fail(SVC_ERR_INVALID_ARG, "mv block height must be divisible by transform block height");
+  if (cfg->frame_w == 0 || cfg->frame_h == 0) return fail(SVC_ERR_INVALID_ARG, "frame dimensions must be > 0");
+  const uint32_t pw = svc_padded_dim(cfg->frame_w, cfg->mv_block_w, cfg->pyr_lvl_count);
+  const uint32_t ph = svc_padded_dim(cfg->frame_h, cfg->mv_block_h, cfg->pyr_lvl_count);
+  int rc = check_hbma_args(cfg->pyr_lvl_count, pw, ph, cfg->mv_search_range, cfg->mv_block_w,
+                           cfg->mv_block_h, false);
+  if (rc) return rc;
+  rc = check_dct_args(cfg->frame_w, cfg->frame_h, pw, ph, cfg->transform_block_w, cfg->transform_block_h);
+  if (rc) return rc;
+  rc = prepare_device(cfg->device);
+  if (rc) return rc;
+
+  svc_session* s = new svc_session();
+  s->cfg = *cfg;
+  s->device = cfg->device;
+  s->info.padded_w = pw;
+  s->info.padded_h = ph;
+  s->info.mv_field_w = pw / cfg->mv_block_w;
+  s->info.mv_field_h = ph / cfg->mv_block_h;
+  s->info.frame_in_bytes = (uint64_t)cfg->frame_w * cfg->frame_h * 3;
+  s->info.frame_stream_bytes = svc_serialized_frame_bytes(cfg->frame_w, cfg->frame_h,
+                                                          cfg->transform_block_w,
+                                                          cfg->transform_block_h, 3);
+  s->info.record_bytes = 4 + 3 * cfg->transform_block_w * cfg->transform_block_h * 4;
+  s->info.max_batch = cfg->max_batch ? cfg->max_batch : 32;
+  s->lay = make_pyr_layout(pw, ph, cfg->pyr_lvl_count);
+  auto bail = [&](int code) {
+    svc_session_destroy(s);
+    return code;
+  };
+  cudaError_t e;
+  if (cfg->cuda_stream) {
+    s->stream = static_cast<cudaStream_t>(cfg->cuda_stream);
+  } else {
+    e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
+    s->own_stream = true;
+  }
+  e = cudaMalloc(&s->d_pyr, (size_t)(s->info.max_batch + 1) * s->lay.slot_bytes + kSlack);
+  if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(pyramids)"));
+  e = cudaMemsetAsync(s->d_pyr, 0, (size_t)(s->info.max_batch + 1) * s->lay.slot_bytes + kSlack, s->stream);
+  if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemset(pyramids)"));
+  if (needs_scratch(s)) {
+    s->scratch_frames = std::min<uint32_t>(s->info.max_batch, 4);
+    e = cudaMalloc(&s->d_scratch, (size_t)s->scratch_frames * 6 * pw * ph * sizeof(float));
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(scratch)"));
+  }
+  *out = s;
+  return SVC_OK;
+}
+
+void svc_session_destroy(svc_session* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(s->d_in[b]);
+    cudaFree(s->d_mv[b]);
+    cudaFree(s->d_mad[b]);
+    cudaFree(s->d_st[b]);
+    cudaFree(s->d_bt[b]);
+    if (s->ev_in[b]) cudaEventDestroy(s->ev_in[b]);
+    if (s->ev_comp[b]) cudaEventDestroy(s->ev_comp[b]);
+    if (s->ev_out[b]) cudaEventDestroy(s->ev_out[b]);
+  }
+  cudaFree(s->d_pyr);
+  cudaFree(s->d_scratch);
+  if (s->s_in) cudaStreamDestroy(s->s_in);
+  if (s->s_out) cudaStreamDestroy(s->s_out);
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  cudaGetLastError();
+  delete s;
+}
+
+int svc_session_info_get(const svc_session* s, svc_session_info* out) {
+  if (!s || !out) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  *out = s->info;
+  return SVC_OK;
+}
+
+int svc_session_reset(svc_session* s) {
+  if (!s) return fail(SVC_ERR_INVALID_ARG, "null session");
+  s->have_prev = false;
+  return SVC_OK;
+}
+
+uint64_t svc_session_launch_count(const svc_session* s) { return s ? s->launches : 0; }
+
+int svc_session_synchronize(svc_session* s) {
+  if (!s) return fail(SVC_ERR_INVALID_ARG, "null session");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  return SVC_OK;
+}
+
+int svc_session_encode_device(svc_session* s, const uint8_t* d_frames, uint32_t n_frames,
+                              float* d_mv, float* d_mad, uint8_t* d_stream,
+                              const uint32_t* d_bt, uint32_t* n_encoded) {
+  if (!s) return fail(SVC_ERR_INVALID_ARG, "null session");
+  if (n_encoded) *n_encoded = 0;
+  if (n_frames == 0) return SVC_OK;
+  if (!d_frames) return fail(SVC_ERR_INVALID_ARG, "null frames");
+  CU(cudaSetDevice(s->device));
+  const size_t mvn = (size_t)s->info.mv_field_w * s->info.mv_field_h;
+  uint32_t done_in = 0, done_enc = 0;
+  while (done_in < n_frames) {
+    const uint32_t m = std::min(s->info.max_batch, n_frames - done_in);
+    uint32_t ne = 0;
+    int rc = encode_batch_device(
+        s, d_frames + (size_t)done_in * s->info.frame_in_bytes, m,
+        d_mv ? d_mv + done_enc * mvn * 2 : nullptr, d_mad ? d_mad + done_enc * mvn : nullptr,
+        d_stream ? d_stream + (size_t)done_enc * s->info.frame_stream_bytes : nullptr,
+        d_bt ? d_bt + done_enc * mvn : nullptr, &ne);
+    if (rc) return rc;
+    done_in += m;
+    done_enc += ne;
+  }
+  if (n_encoded) *n_encoded = done_enc;
+  return SVC_OK;
+}
+
+int svc_session_encode(svc_session* s, const uint8_t* frames, uint32_t n_frames, float* mv,
+                       float* mad, uint8_t* stream, const uint32_t* block_types,
+                       uint32_t* n_encoded) {
+  if (!s) return fail(SVC_ERR_INVALID_ARG, "null session");
+  if (n_encoded) *n_encoded = 0;
+  if (n_frames == 0) return SVC_OK;
+  if (!frames) return fail(SVC_ERR_INVALID_ARG, "null frames");
+  CU(cudaSetDevice(s->device));
+  int rc = ensure_staging(s);
+  if (rc) return rc;
+  const size_t mvn = (size_t)s->info.mv_field_w * s->info.mv_field_h;
+  const size_t fin = s->info.frame_in_bytes, fst = s->info.frame_stream_bytes;
+  uint32_t done_in = 0, done_enc = 0, chunk = 0;
+  // 3-stage pipeline over batches: H2D (s_in) | kernels (stream) | D2H (s_out)
+  while (done_in < n_frames) {
+    const int b = chunk & 1;
+    const uint32_t m = std::min(s->info.max_batch, n_frames - done_in);
+    const uint32_t ne = s->have_prev ? m : m - 1;
+    if (chunk >= 2) {
+      CU(cudaStreamWaitEvent(s->s_in, s->ev_comp[b], 0));   // d_in[b] consumed
+      CU(cudaStreamWaitEvent(s->stream, s->ev_out[b], 0));  // outputs[b] drained
+    }
+    CU(cudaMemcpyAsync(s->d_in[b], frames + (size_t)done_in * fin, (size_t)m * fin,
+                       cudaMemcpyHostToDevice, s->s_in));
+    if (block_types && ne)
+      CU(cudaMemcpyAsync(s->d_bt[b], block_types + done_enc * mvn, ne * mvn * sizeof(uint32_t),
+                         cudaMemcpyHostToDevice, s->s_in));
+    CU(cudaEventRecord(s->ev_in[b], s->s_in));
+    CU(cudaStreamWaitEvent(s->stream, s->ev_in[b], 0));
+    uint32_t ne2 = 0;
+    rc = encode_batch_device(s, s->d_in[b], m, (mv || mad) ? s->d_mv[b] : nullptr,
+                             mad ? s->d_mad[b] : nullptr, stream ? s->d_st[b] : nullptr,
+                             block_types ? s->d_bt[b] : nullptr, &ne2);
+    if (rc) return rc;
+    CU(cudaEventRecord(s->ev_comp[b], s->stream));
+    CU(cudaStreamWaitEvent(s->s_out, s->ev_comp[b], 0));
+    if (ne2) {
+      if (mv)
+        CU(cudaMemcpyAsync(mv + done_enc * mvn * 2, s->d_mv[b], ne2 * mvn * sizeof(float2),
+                           cudaMemcpyDeviceToHost, s->s_out));
+      if (mad)
+        CU(cudaMemcpyAsync(mad + done_enc * mvn, s->d_mad[b], ne2 * mvn * sizeof(float),
+                           cudaMemcpyDeviceToHost, s->s_out));
+      if (stream)
+        CU(cudaMemcpyAsync(stream + (size_t)done_enc * fst, s->d_st[b], (size_t)ne2 * fst,
+                           cudaMemcpyDeviceToHost, s->s_out));
+    }
+    CU(cudaEventRecord(s->ev_out[b], s->s_out));
+    done_in += m;
+    done_enc += ne2;
+    ++chunk;
+  }
+  CU(cudaStreamSynchronize(s->s_in));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaStreamSynchronize(s->s_out));
+  if (n_encoded) *n_encoded = done_enc;
+  return SVC_OK;
+}
+
+int svc_session_run_stage(svc_session* s, int stage, const uint8_t* d_frames, uint32_t n_frames,
+                          float* d_mv, float* d_mad, uint8_t* d_stream) {
+  if (!s) return fail(SVC_ERR_INVALID_ARG, "null session");
+  if (n_frames == 0 || n_frames > s->info.max_batch)
+    return fail(SVC_ERR_INVALID_ARG, "n_frames must be in [1, max_batch]");
+  CU(cudaSetDevice(s->device));
+  int nl = 0;
+  switch (stage) {
+    case SVC_STAGE_Y_PYRAMID: {
+      if (!d_frames) return fail(SVC_ERR_INVALID_ARG, "null frames");
+      CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, s->d_pyr, s->lay, 1, n_frames, s->stream));
+      nl += 1;
+      for (uint32_t l = 0; l + 1 < s->lay.levels; ++l) {
+        CU(launch_pyr_down(s->d_pyr, s->lay, l, 1, n_frames, s->stream));
+        nl += 1;
+      }
+      break;
+    }
+    case SVC_STAGE_HBMA: {
+      HbmaParams p{};
+      p.pyr = s->d_pyr;
+      p.lay = s->lay;
+      p.bw = s->cfg.mv_block_w;
+      p.bh = s->cfg.mv_block_h;
+      p.r = s->cfg.mv_search_range >> (s->cfg.pyr_lvl_count - 1);
+      p.mvw = s->info.mv_field_w;
+      p.mvh = s->info.mv_field_h;
+      p.mv = reinterpret_cast<float2*>(d_mv);
+      p.mad = d_mad;
+      p.n_frames = n_frames;
+      CU(launch_hbma(p, s->stream, &nl));
+      break;
+    }
+    case SVC_STAGE_DCT_STREAM: {
+      if (!d_frames || !d_stream) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+      DctParams p{};
+      p.bgr = d_frames;
+      p.w = s->cfg.frame_w; p.h = s->cfg.frame_h;
+      p.pw = s->info.padded_w; p.ph = s->info.padded_h;
+      p.tbw = s->cfg.transform_block_w; p.tbh = s->cfg.transform_block_h;
+      p.n_frames = n_frames;
+      p.stream = d_stream;
+      p.frame_stream_bytes = s->info.frame_stream_bytes;
+      p.mv_block_w = s->cfg.mv_block_w; p.mv_block_h = s->cfg.mv_block_h;
+      p.mv_field_w = s->info.mv_field_w; p.mv_field_h = s->info.mv_field_h;
+      p.scratch_planes = s->d_scratch;
+      p.scratch_frames = s->scratch_frames;
+      CU(launch_dct(p, s->stream, &nl));
+      break;
+    }
+    default:
+      return fail(SVC_ERR_INVALID_ARG, "unknown stage");
+  }
+  s->launches += (uint64_t)nl;
+  return SVC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,261 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle, the
+golden fixtures (compiled reference + cv2) and, where it travelled, the
+compiled reference itself.  Integer work is bit-exact; DCT coefficients are
+within DCT_TOL absolute of OpenCV / the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from svc_b200.synth import SyntheticSequence
+
+pytestmark = pytest.mark.gpu
+
+DCT_TOL = 1e-3  # absolute, per coefficient (coefficients reach 2040)
+
+
+# ---------------------------------------------------------------- K1: Y pyramid
+@pytest.mark.parametrize("name,n", [("small_default.npz", 3), ("aligned_default.npz", 2)])
+def test_y_pyramid_golden(gpu, name, n):
+    g = load_golden(name)
+    for i in range(n):
+        pyr = gpu.y_pyramid(g["frames"][i], int(g["pw"]), int(g["ph"]), 4)
+        for l in range(4):
+            assert np.array_equal(pyr[l], g[f"pyr{i}_{l}"]), (name, i, l)
+
+
+@pytest.mark.parametrize("w,h,L,B", [(1920, 1080, 4, 16), (960, 540, 4, 16), (333, 77, 3, 8),
+                                     (16, 16, 4, 16), (50, 34, 2, 2), (8, 8, 1, 8), (130, 70, 5, 16)])
+def test_y_pyramid_vs_oracle(gpu, oracle, w, h, L, B):
+    rng = np.random.default_rng(w * 7 + h)
+    f = rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8)
+    pw, ph = gpu.padded_dim(w, B, L), gpu.padded_dim(h, B, L)
+    got, exp = gpu.y_pyramid(f, pw, ph, L), oracle.y_pyramid(f, pw, ph, L)
+    for l in range(L):
+        assert np.array_equal(got[l], exp[l]), l
+
+
+# ---------------------------------------------------------------- K2: motion
+def test_hbma_golden_default(gpu):
+    g = load_golden("small_default.npz")
+    for i in (1, 2):
+        t = [g[f"pyr{i-1}_{l}"] for l in range(4)]
+        a = [g[f"pyr{i}_{l}"] for l in range(4)]
+        mv, mad = gpu.EstimateMotionHierarchical16x16Sse2(t, a, int(g["pw"]), int(g["ph"]), 8)
+        assert np.array_equal(mv, g[f"mv{i}"]) and np.array_equal(mad, g[f"mad{i}"])
+        mv, mad = gpu.EstimateMotionHierarchical(t, a, 4, int(g["pw"]), int(g["ph"]), 8, 16, 16)
+        assert np.array_equal(mv, g[f"mv{i}"]) and np.array_equal(mad, g[f"mad{i}"])
+
+
+@pytest.mark.parametrize("R", [8, 16, 32])
+def test_hbma_golden_ranges(gpu, R):
+    g = load_golden("aligned_default.npz")
+    t = [g[f"pyr0_{l}"] for l in range(4)]
+    a = [g[f"pyr1_{l}"] for l in range(4)]
+    mv, mad = gpu.EstimateMotionHierarchical16x16Sse2(t, a, int(g["pw"]), int(g["ph"]), R)
+    assert np.array_equal(mv, g[f"mv_R{R}"]) and np.array_equal(mad, g[f"mad_R{R}"])
+
+
+def test_hbma_golden_generic(gpu):
+    g = load_golden("generic_motion.npz")
+    for ci, (lv, bw, bh, rr) in enumerate(g["cases"]):
+        t = [g[f"t{ci}_{l}"] for l in range(lv)]
+        a = [g[f"a{ci}_{l}"] for l in range(lv)]
+        fh, fw = t[0].shape
+        mv, mad = gpu.EstimateMotionHierarchical(t, a, int(lv), fw, fh, int(rr), int(bw), int(bh))
+        assert np.array_equal(mv, g[f"mv{ci}"]), ci
+        assert np.array_equal(mad, g[f"mad{ci}"]), ci
+    fh, fw = g["t3"].shape
+    mv, mad = gpu.EstimateMotionExhaustiveSearch(g["t3"], g["a3"], fw, fh, 3, 8, 8)
+    assert np.array_equal(mv, g["ebma_mv"]) and np.array_equal(mad, g["ebma_mad"])
+
+
+@pytest.mark.parametrize("w,h,R,seed", [(960, 540, 8, 1), (960, 540, 32, 2), (320, 180, 16, 3),
+                                        (64, 48, 8, 4), (16, 16, 8, 5), (1920, 1080, 8, 6)])
+def test_hbma_vs_oracle_synthetic(gpu, oracle, w, h, R, seed):
+    pw, ph = gpu.padded_dim(w, 16, 4), gpu.padded_dim(h, 16, 4)
+    seq = SyntheticSequence(w, h, 2, seed=seed)
+    p0, p1 = oracle.y_pyramid(seq.frame(0), pw, ph, 4), oracle.y_pyramid(seq.frame(1), pw, ph, 4)
+    mv, mad = gpu.EstimateMotionHierarchical16x16Sse2(p0, p1, pw, ph, R)
+    emv, emad = oracle.hbma(p0, p1, R)
+    assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+    if oracle.have_ref():
+        rmv, rmad = oracle.hbma(p0, p1, R, impl="ref_sse2")
+        assert np.array_equal(mv, rmv) and np.array_equal(mad, rmad)
+
+
+@pytest.mark.parametrize("L,bw,bh,R", [(1, 16, 16, 5), (2, 8, 8, 9), (3, 32, 16, 12),
+                                       (5, 16, 16, 16), (2, 6, 10, 7), (1, 3, 7, 1), (4, 64, 64, 8)])
+def test_hbma_vs_oracle_generic(gpu, oracle, L, bw, bh, R):
+    w, h = bw * 7, bh * 5
+    pw, ph = gpu.padded_dim(w, bw, L), gpu.padded_dim(h, bh, L)
+    seq = SyntheticSequence(w, h, 2, seed=bw + bh + L, n_rects=2)
+    p0, p1 = oracle.y_pyramid(seq.frame(0), pw, ph, L), oracle.y_pyramid(seq.frame(1), pw, ph, L)
+    mv, mad = gpu.EstimateMotionHierarchical(p0, p1, L, pw, ph, R, bw, bh)
+    emv, emad = oracle.hbma(p0, p1, R, bw, bh)
+    assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+
+
+def test_hbma_flat_frames_tie_break(gpu, oracle):
+    z = [np.zeros((64 >> l, 96 >> l), np.uint8) for l in range(4)]
+    c = [np.full((64 >> l, 96 >> l), 9, np.uint8) for l in range(4)]
+    for t, a in ((z, z), (z, c), (c, z)):
+        mv, mad = gpu.EstimateMotionHierarchical16x16Sse2(t, a, 96, 64, 8)
+        emv, emad = oracle.hbma(t, a, 8)
+        assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+        assert not mv.any()
+
+
+def test_ebma_zero_range(gpu, oracle):
+    rng = np.random.default_rng(3)
+    t = rng.integers(0, 256, size=(32, 48)).astype(np.uint8)
+    a = rng.integers(0, 256, size=(32, 48)).astype(np.uint8)
+    mv, mad = gpu.EstimateMotionExhaustiveSearch(t, a, 48, 32, 0, 8, 8)
+    emv, emad = oracle.ebma(t, a, 0, 8, 8)
+    assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+
+
+# ---------------------------------------------------------------- K3: DCT + stream
+@pytest.mark.parametrize("name", ["small_default.npz", "aligned_default.npz"])
+def test_dct_planar_golden(gpu, name):
+    g = load_golden(name)
+    d = gpu.dct_planar(g["frames"][1], int(g["pw"]), int(g["ph"]))
+    assert np.abs(d - g["dct1"]).max() <= DCT_TOL
+
+
+def test_dct_known_answers(gpu):
+    g = load_golden("dct_kat.npz")
+    for key, tbw, tbh in (("8", 8, 8), ("4", 4, 4), ("16", 16, 16), ("48", 8, 4)):
+        for b, o in zip(g["b" + key], g["o" + key]):
+            bgr = np.repeat(b.astype(np.uint8)[..., None], 3, axis=2)
+            d = gpu.dct_planar(bgr, tbw, tbh, tbw, tbh)
+            for c in range(3):
+                assert np.abs(d[c] - o).max() <= DCT_TOL, (key, c)
+
+
+@pytest.mark.parametrize("w,h,tbw,tbh", [(1920, 1080, 8, 8), (104, 56, 8, 8), (96, 48, 4, 4),
+                                         (64, 64, 16, 16), (80, 48, 8, 4), (48, 80, 2, 16)])
+def test_dct_planar_vs_oracle(gpu, oracle, w, h, tbw, tbh):
+    rng = np.random.default_rng(w + h + tbw)
+    f = rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8)
+    pw, ph = gpu.padded_dim(w, 16, 4), gpu.padded_dim(h, 16, 4)
+    d = gpu.dct_planar(f, pw, ph, tbw, tbh)
+    e = oracle.dct_planar(f, pw, ph, tbw, tbh)
+    assert np.abs(d - e).max() <= DCT_TOL
+
+
+def _stream_check(gpu, oracle, f, pw, ph, tbw, tbh, bt):
+    h, w, _ = f.shape
+    st = gpu.encode_frame_stream(f, pw, ph, tbw, tbh, 16, 16, bt)
+    planes = oracle.dct_planar(f, pw, ph, tbw, tbh)
+    exp = oracle.serialize_frame(planes, bt, w, h, tbw, tbh, pw // 16, 16, 16)
+    assert st.size == exp.size
+    rec = 1 + 3 * tbw * tbh
+    got_w = st.view(np.uint32).reshape(-1, rec)
+    exp_w = exp.view(np.uint32).reshape(-1, rec)
+    assert np.array_equal(got_w[:, 0], exp_w[:, 0])  # block types: exact
+    assert np.abs(got_w[:, 1:].view(np.float32) - exp_w[:, 1:].view(np.float32)).max() <= DCT_TOL
+
+
+@pytest.mark.parametrize("w,h,tbw,tbh", [(160, 92, 8, 8), (104, 56, 8, 8), (1920, 1080, 8, 8),
+                                         (960, 540, 8, 8), (48, 40, 8, 8), (96, 48, 4, 4),
+                                         (80, 48, 8, 4), (100, 36, 16, 16)])
+def test_stream_layout_vs_oracle(gpu, oracle, w, h, tbw, tbh):
+    rng = np.random.default_rng(w * 3 + h + tbw)
+    f = rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8)
+    pw, ph = gpu.padded_dim(w, 16, 4), gpu.padded_dim(h, 16, 4)
+    bt = rng.integers(0, 11, size=(ph // 16) * (pw // 16)).astype(np.uint32)
+    _stream_check(gpu, oracle, f, pw, ph, tbw, tbh, bt)
+    _stream_check(gpu, oracle, f, pw, ph, tbw, tbh, None)
+
+
+# ---------------------------------------------------------------- session
+@pytest.mark.parametrize("w,h,n,batch", [(960, 540, 6, 4), (104, 56, 5, 2), (160, 92, 4, 32)])
+def test_session_host_path_matches_oracle(gpu, oracle, w, h, n, batch):
+    seq = SyntheticSequence(w, h, n, seed=21)
+    frames = seq.frames()
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, max_batch=batch)) as s:
+        pw, ph = s.padded_w, s.padded_h
+        rng = np.random.default_rng(9)
+        bt = rng.integers(0, 6, size=(n - 1, s.mv_field_h * s.mv_field_w)).astype(np.uint32)
+        # feed in two uneven pushes: exercises the resident previous pyramid
+        mv1, mad1, st1 = s.encode(frames[:2], block_types=bt[:1])
+        mv2, mad2, st2 = s.encode(frames[2:], block_types=bt[1:])
+        mv = np.concatenate([mv1, mv2]); mad = np.concatenate([mad1, mad2]); st = np.concatenate([st1, st2])
+        assert mv.shape[0] == n - 1
+        pyr = [oracle.y_pyramid(f, pw, ph, 4) for f in frames]
+        for i in range(1, n):
+            emv, emad = oracle.hbma(pyr[i - 1], pyr[i], 8)
+            assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad), i
+            planes = oracle.dct_planar(frames[i], pw, ph)
+            exp = oracle.serialize_frame(planes, bt[i - 1], w, h, 8, 8, pw // 16, 16, 16)
+            g = st[i - 1].view(np.uint32).reshape(-1, 193)
+            e = exp.view(np.uint32).reshape(-1, 193)
+            assert np.array_equal(g[:, 0], e[:, 0])
+            assert np.abs(g[:, 1:].view(np.float32) - e[:, 1:].view(np.float32)).max() <= DCT_TOL
+        assert s.launch_count > 0
+
+
+def test_session_device_path_full_1080p_properties(gpu, oracle):
+    """BASELINE config 2 geometry on the device-resident path: a few frames are
+    checked exactly against the oracle, the rest through properties that do
+    not need the oracle (static repeat -> zero motion and zero MAD; DC
+    coefficient = 8 * block mean)."""
+    w, h, n = 1920, 1080, 12
+    seq = SyntheticSequence(w, h, n, seed=5)
+    frames = seq.frames()
+    frames[7] = frames[6]  # a repeated frame: exact zero-motion / zero-MAD property
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, max_batch=5)) as s:
+        mvn = s.mv_field_w * s.mv_field_h
+        d_in = gpu.DeviceBuffer(0, frames.nbytes)
+        d_mv = gpu.DeviceBuffer(0, (n - 1) * mvn * 8)
+        d_mad = gpu.DeviceBuffer(0, (n - 1) * mvn * 4)
+        d_st = gpu.DeviceBuffer(0, (n - 1) * s.frame_stream_bytes)
+        d_in.upload(frames)
+        ne = s.encode_device(d_in, n, d_mv, d_mad, d_st)
+        s.synchronize()
+        assert ne == n - 1
+        mv = d_mv.download(np.float32, (n - 1, s.mv_field_h, s.mv_field_w, 2))
+        mad = d_mad.download(np.float32, (n - 1, s.mv_field_h, s.mv_field_w))
+        st = d_st.download(np.uint8, (n - 1, s.frame_stream_bytes))
+        pw, ph = s.padded_w, s.padded_h
+        for i in (1, 6, 11):
+            p0, p1 = oracle.y_pyramid(frames[i - 1], pw, ph, 4), oracle.y_pyramid(frames[i], pw, ph, 4)
+            emv, emad = oracle.hbma(p0, p1, 8)
+            assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad)
+        # frame 7 == frame 6: every block matches itself exactly
+        assert not mad[6].any()
+        # DC term of every 8x8 block and channel = sum / 8
+        rec = st.view(np.uint32).reshape(n - 1, 135, 240, 193)
+        assert not rec[..., 0].any()
+        for i in (2, 9):
+            dc = rec[i - 1][..., 1::64].view(np.float32)  # (135, 240, 3)
+            exp = frames[i].reshape(135, 8, 240, 8, 3).astype(np.float64).sum(axis=(1, 3)) / 8.0
+            assert np.abs(dc - exp).max() <= DCT_TOL
+        planes = oracle.dct_planar(frames[4], pw, ph)
+        exp = oracle.serialize_frame(planes, None, w, h, 8, 8, pw // 16, 16, 16)
+        assert np.abs(st[3].view(np.float32) - exp.view(np.float32)).max() <= DCT_TOL
+        for b in (d_in, d_mv, d_mad, d_st):
+            b.free()
+
+
+def test_stage_entry_points(gpu, oracle):
+    w, h, n = 320, 180, 3
+    seq = SyntheticSequence(w, h, n, seed=8)
+    frames = seq.frames()
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, max_batch=4)) as s:
+        mvn = s.mv_field_w * s.mv_field_h
+        d_in = gpu.DeviceBuffer(0, frames.nbytes)
+        d_mv = gpu.DeviceBuffer(0, n * mvn * 8)
+        d_mad = gpu.DeviceBuffer(0, n * mvn * 4)
+        d_st = gpu.DeviceBuffer(0, n * s.frame_stream_bytes)
+        d_in.upload(frames)
+        s.run_stage(gpu.STAGE_Y_PYRAMID, d_in, n)
+        s.run_stage(gpu.STAGE_HBMA, None, n, d_mv, d_mad)
+        s.run_stage(gpu.STAGE_DCT_STREAM, d_in, n, None, None, d_st)
+        s.synchronize()
+        mv = d_mv.download(np.float32, (n, s.mv_field_h, s.mv_field_w, 2))
+        pw, ph = s.padded_w, s.padded_h
+        pyr = [oracle.y_pyramid(f, pw, ph, 4) for f in frames]
+        for i in (1, 2):  # slot i+1 vs slot i  (slot 0 is the zero-initialised previous frame)
+            emv, _ = oracle.hbma(pyr[i - 1], pyr[i], 8)
+            assert np.array_equal(mv[i], emv)
