@@ -56,6 +56,7 @@ struct HbmaParams {
   float2* mv;   // n_frames x mvh x mvw, may be null
   float* mad;   // n_frames x mvh x mvw, may be null
   uint32_t n_frames;
+  uint32_t force_generic;  // 1 = always take the universal kernel (tests)
 };
 cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches);
 

@@ -15,7 +15,9 @@
 //   * MAD = (float)sad / (float)(bw*bh) (:38-40), IEEE division.
 // Within one level integer SAD order equals float MAD order (sad < 2^23), so
 // the argmin runs on integers and only the winner is converted.
+#include <cuda.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -137,8 +139,324 @@ hbma_generic_kernel(HbmaParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Tiled fast path (16x16 blocks, small top-level range: the encoder default
+// R=8/L=4 -> r=1, and the low-r corner of the range sweep).
+//
+// A CTA owns a tile of TBX x 4 motion blocks.  Because the reach of the search
+// at level l is bounded by d_l = r (2^(L-l) - 1), the whole reference-frame
+// search window of the tile -- every level, halo included -- is known up front:
+// one elected thread stages it (and the anchor tile) in shared memory with TMA
+// tensor loads (cp.async.bulk.tensor.3d; box origin floored to 16 bytes in x as
+// the TMA unit requires; out-of-frame bytes zero-filled but
+// never used: candidates are clamped to the frame exactly like the reference,
+// libs/motion.cpp:297-310, 375-385), all signalled on one mbarrier.  Then every
+// warp walks one tile row down the pyramid with no further block-wide sync.
+//
+// Lane mapping: 2r+1 lanes per motion block, one per candidate column dx.  A
+// lane streams the B+2r tracked rows of its column once (aligned words +
+// funnel shift), keeps the anchor block in registers and feeds 2r+1 running
+// SADs (one per dy) with packed-byte VABSDIFF4.  The argmin is a packed
+// (sad << 8 | scan index) minimum over the group's lanes, which reproduces the
+// reference's first-minimum rule; the top level gathers all (2r+1)^2 SADs and
+// replays the reference's "<=" scan (last minimum wins, all-updates => zero).
+// ---------------------------------------------------------------------------
+__host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+template <int L, int R>
+struct TileGeom {
+  static constexpr int G = 2 * R + 1;   // lanes per motion block
+  static constexpr int BPW = 32 / G;    // motion blocks per warp
+  static constexpr int TBX = BPW, TBY = 4;
+  static constexpr int kThreads = TBY * 32;
+  __host__ __device__ static constexpr int b(int l) { return 16 >> l; }
+  __host__ __device__ static constexpr int d(int l) { return R * ((1 << (L - l)) - 1); }
+  // TMA needs the box start 16-byte aligned in the innermost dimension: the box is
+  // anchored at floor16(x) and widened by up to 15 bytes.
+  __host__ __device__ static constexpr int tw(int l) { return align_up(TBX * b(l) + 2 * d(l) + 15, 16); }
+  __host__ __device__ static constexpr int th(int l) { return TBY * b(l) + 2 * d(l); }
+  __host__ __device__ static constexpr int aw(int l) {
+    return (TBX * b(l)) % 16 == 0 ? TBX * b(l) : align_up(TBX * b(l) + 15, 16);
+  }
+  __host__ __device__ static constexpr int ah(int l) { return TBY * b(l); }
+  __host__ __device__ static constexpr int off_t(int l) {
+    int o = 0;
+    for (int i = 0; i < l; ++i) o += align_up(tw(i) * th(i), 128) + align_up(aw(i) * ah(i), 128);
+    return o;
+  }
+  __host__ __device__ static constexpr int off_a(int l) { return off_t(l) + align_up(tw(l) * th(l), 128); }
+  __host__ __device__ static constexpr int smem_bytes() { return off_t(L) + 128; }
+  __host__ __device__ static constexpr int tx_bytes() {
+    int o = 0;
+    for (int i = 0; i < L; ++i) o += tw(i) * th(i) + aw(i) * ah(i);
+    return o;
+  }
+  __host__ __device__ static constexpr bool ok() {
+    return tw(0) <= 256 && th(0) <= 256 && smem_bytes() <= 100 * 1024 && BPW >= 1;
+  }
+};
+
+template <int B, int R>
+__device__ __forceinline__ void sad_column(const uint8_t* __restrict__ tcol, const int PT,
+                                           const int sx, const uint8_t* __restrict__ ablk,
+                                           const int PA, uint32_t (&acc)[2 * R + 1]) {
+  constexpr int NW = B >= 4 ? B / 4 : 1;
+  constexpr uint32_t MASK = B >= 4 ? 0xffffffffu : (B == 2 ? 0xffffu : 0xffu);
+  uint32_t a[B][NW];
+#pragma unroll
+  for (int k = 0; k < B; ++k) {
+    const uint8_t* q = ablk + k * PA;
+    if constexpr (B == 16) {
+      const uint4 v = *reinterpret_cast<const uint4*>(q);
+      a[k][0] = v.x; a[k][1] = v.y; a[k][2] = v.z; a[k][3] = v.w;
+    } else if constexpr (B == 8) {
+      const uint2 v = *reinterpret_cast<const uint2*>(q);
+      a[k][0] = v.x; a[k][1] = v.y;
+    } else if constexpr (B == 4) {
+      a[k][0] = *reinterpret_cast<const uint32_t*>(q);
+    } else if constexpr (B == 2) {
+      a[k][0] = *reinterpret_cast<const uint16_t*>(q);
+    } else {
+      a[k][0] = *q;
+    }
+  }
+  const uint8_t* trow = tcol + (sx & ~3);
+  const uint32_t sh = (uint32_t)(sx & 3) * 8u;
+#pragma unroll
+  for (int t = 0; t < B + 2 * R; ++t) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(trow + t * PT);
+    uint32_t raw[NW + 1];
+#pragma unroll
+    for (int k = 0; k <= NW; ++k) raw[k] = q[k];
+    uint32_t tw[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) tw[k] = __funnelshift_r(raw[k], raw[k + 1], sh) & MASK;
+#pragma unroll
+    for (int dyi = 0; dyi <= 2 * R; ++dyi) {
+      const int ar = t - dyi;
+      if (ar >= 0 && ar < B) {
+#pragma unroll
+        for (int k = 0; k < NW; ++k) acc[dyi] = __vsadu4(tw[k], a[ar][k]) + acc[dyi];
+      }
+    }
+  }
+}
+
+struct HbmaTileMaps {
+  CUtensorMap t[5];  // tracked-window boxes, per level
+  CUtensorMap a[5];  // anchor-tile boxes, per level
+};
+
+template <int L, int R, int LV>
+__device__ __forceinline__ void tile_level(const uint8_t* smem, const HbmaParams& p, const int g,
+                                           const int dxi, const int w, const int tile_bx0,
+                                           const int tile_by0, int& mx, int& my, float& cur) {
+  using Gm = TileGeom<L, R>;
+  constexpr int G = Gm::G;
+  constexpr int B = 16 >> LV;
+  constexpr int D = Gm::d(LV);
+  constexpr bool TOP = (LV == L - 1);
+  constexpr int PT = Gm::tw(LV), PA = Gm::aw(LV);
+  const uint8_t* sT = smem + Gm::off_t(LV);
+  const uint8_t* sA = smem + Gm::off_a(LV);
+  const int fw = (int)p.lay.w[LV], fh = (int)p.lay.h[LV];
+  if (!TOP) { mx *= 2; my *= 2; }
+  const int ax = (tile_bx0 + g) * B, ay = (tile_by0 + w) * B;
+  const int cx = ax + mx, cy = ay + my;
+  const int x = cx - R + dxi;
+  const int sx = x - ((tile_bx0 * B - D) & ~15);  // box starts at floor16
+  const int sy0 = (cy - R) - (tile_by0 * B - D);
+  uint32_t acc[G];
+#pragma unroll
+  for (int i = 0; i < G; ++i) acc[i] = 0;
+  sad_column<B, R>(sT + sy0 * PT, PT, sx, sA + (w * B) * PA + ((tile_bx0 * B) & 15) + g * B, PA, acc);
+  const bool xok = (x >= 0) && (x <= fw - B);
+  const int gbase = g * G;
+  constexpr float inv_area = 1.0f / (float)(B * B);
+  if constexpr (TOP) {
+    const uint32_t xmask = __ballot_sync(0xffffffffu, xok) >> gbase;
+    uint32_t best_s = 0xffffffffu;
+    int best_i = 0;
+    bool all_upd = true;
+#pragma unroll
+    for (int dy = 0; dy < G; ++dy) {
+      const int y = cy - R + dy;
+      const bool yok = (y >= 0) && (y <= fh - B);
+#pragma unroll
+      for (int dj = 0; dj < G; ++dj) {
+        const uint32_t s = __shfl_sync(0xffffffffu, acc[dy], gbase + dj);
+        if (yok && ((xmask >> dj) & 1u)) {
+          if (s <= best_s) { best_s = s; best_i = dy * G + dj; }
+          else all_upd = false;
+        }
+      }
+    }
+    cur = (float)best_s * inv_area;
+    mx = all_upd ? 0 : (best_i % G) - R;
+    my = all_upd ? 0 : (best_i / G) - R;
+  } else {
+    uint32_t key = 0xffffffffu;
+#pragma unroll
+    for (int dy = 0; dy < G; ++dy) {
+      const int y = cy - R + dy;
+      if (xok && y >= 0 && y <= fh - B) key = min(key, (acc[dy] << 8) | (uint32_t)(dy * G + dxi));
+    }
+    uint32_t best = 0xffffffffu;
+#pragma unroll
+    for (int dj = 0; dj < G; ++dj) best = min(best, __shfl_sync(0xffffffffu, key, gbase + dj));
+    if (best != 0xffffffffu) {
+      const float m = (float)(best >> 8) * inv_area;
+      if (m < cur) {
+        const int idx = (int)(best & 0xffu);
+        cur = m;
+        mx = mx - R + idx % G;
+        my = my - R + idx / G;
+      }
+    }
+  }
+}
+
+template <int L, int R>
+__global__ void __launch_bounds__(TileGeom<L, R>::kThreads)
+hbma_tile_kernel(const __grid_constant__ HbmaTileMaps maps, const HbmaParams p) {
+  using Gm = TileGeom<L, R>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tile_bx0 = blockIdx.x * Gm::TBX, tile_by0 = blockIdx.y * Gm::TBY;
+  const int f = blockIdx.z;
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                 "r"((uint32_t)Gm::tx_bytes()) : "memory");
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const int b = 16 >> l;
+      const uint32_t dt = (uint32_t)__cvta_generic_to_shared(smem + Gm::off_t(l));
+      const uint32_t da = (uint32_t)__cvta_generic_to_shared(smem + Gm::off_a(l));
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(dt), "l"(&maps.t[l]), "r"((tile_bx0 * b - Gm::d(l)) & ~15), "r"(tile_by0 * b - Gm::d(l)),
+          "r"(f), "r"(bar_addr) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(da), "l"(&maps.a[l]), "r"((tile_bx0 * b) & ~15), "r"(tile_by0 * b), "r"(f + 1),
+          "r"(bar_addr) : "memory");
+    }
+  }
+  {  // wait for the tile (phase 0)
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar_addr), "r"(0u) : "memory");
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = min(lane / Gm::G, Gm::BPW - 1);
+  const int dxi = lane - (lane / Gm::G) * Gm::G;
+  const bool owner = (lane / Gm::G) < Gm::BPW && dxi == 0;
+  int mx = 0, my = 0;
+  float cur = FLT_MAX;
+  if constexpr (L >= 5) tile_level<L, R, 4>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
+  if constexpr (L >= 4) tile_level<L, R, 3>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
+  if constexpr (L >= 3) tile_level<L, R, 2>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
+  if constexpr (L >= 2) tile_level<L, R, 1>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
+  tile_level<L, R, 0>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
+  const uint32_t bx = (uint32_t)(tile_bx0 + g), by = (uint32_t)(tile_by0 + w);
+  if (owner && bx < p.mvw && by < p.mvh) {
+    const uint64_t o = ((uint64_t)f * p.mvh + by) * p.mvw + bx;
+    if (p.mv) p.mv[o] = make_float2((float)mx, (float)my);
+    if (p.mad) p.mad[o] = cur;
+  }
+}
+
+// ---- host side: tensor maps + dispatch -----------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static bool encode_box(CUtensorMap* m, const uint8_t* base, uint32_t w, uint32_t h, uint32_t pitch,
+                       uint64_t slot_bytes, uint32_t n_slots, uint32_t box_w, uint32_t box_h) {
+  EncodeTiledFn fn = get_encode_tiled();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {w, h, n_slots};
+  const cuuint64_t strides[2] = {pitch, slot_bytes};
+  const cuuint32_t box[3] = {box_w, box_h, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int L, int R>
+static cudaError_t launch_tile(const HbmaParams& p, cudaStream_t st) {
+  using Gm = TileGeom<L, R>;
+  static_assert(Gm::ok(), "tile geometry does not fit");
+  HbmaTileMaps maps;
+  const uint32_t n_slots = p.n_frames + 1;
+  for (int l = 0; l < L; ++l) {
+    const uint8_t* base = p.pyr + p.lay.off[l];
+    if (!encode_box(&maps.t[l], base, p.lay.w[l], p.lay.h[l], p.lay.pitch[l], p.lay.slot_bytes,
+                    n_slots, Gm::tw(l), Gm::th(l)) ||
+        !encode_box(&maps.a[l], base, p.lay.w[l], p.lay.h[l], p.lay.pitch[l], p.lay.slot_bytes,
+                    n_slots, Gm::aw(l), Gm::ah(l)))
+      return cudaErrorNotSupported;
+  }
+  cudaError_t e = cudaFuncSetAttribute(hbma_tile_kernel<L, R>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::smem_bytes());
+  if (e != cudaSuccess) return e;
+  dim3 grid((p.mvw + Gm::TBX - 1) / Gm::TBX, (p.mvh + Gm::TBY - 1) / Gm::TBY, p.n_frames);
+  hbma_tile_kernel<L, R><<<grid, Gm::kThreads, Gm::smem_bytes(), st>>>(maps, p);
+  return cudaGetLastError();
+}
+
+// (levels, r) pairs with a tiled instantiation; everything else takes the generic kernel
+static bool try_launch_tile(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
+  if (p.bw != 16 || p.bh != 16 || p.n_frames > 65535) return false;
+  if ((p.mvh + 3) / 4 > 65535) return false;
+  const uint32_t L = p.lay.levels, r = p.r;
+#define SVC_TILE_CASE(LL, RR) \
+  if (L == LL && r == RR) { *err = launch_tile<LL, RR>(p, st); return true; }
+  SVC_TILE_CASE(4, 1) SVC_TILE_CASE(4, 2) SVC_TILE_CASE(4, 3) SVC_TILE_CASE(4, 4)
+  SVC_TILE_CASE(3, 1) SVC_TILE_CASE(3, 2) SVC_TILE_CASE(3, 3) SVC_TILE_CASE(3, 4)
+  SVC_TILE_CASE(5, 1) SVC_TILE_CASE(5, 2)
+  SVC_TILE_CASE(2, 1) SVC_TILE_CASE(2, 2) SVC_TILE_CASE(2, 3) SVC_TILE_CASE(2, 4)
+#undef SVC_TILE_CASE
+  return false;
+}
+
 cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches) {
   if (p.n_frames == 0) return cudaSuccess;
+  static const bool env_generic = getenv("SVC_HBMA_FORCE_GENERIC") != nullptr;  // test hook
+  if (!p.force_generic && !env_generic) {
+    cudaError_t e = cudaSuccess;
+    if (try_launch_tile(p, st, &e)) {
+      if (n_launches) *n_launches += 1;
+      return e;
+    }
+  }
+
   const uint64_t warps = (uint64_t)p.mvw * p.mvh * p.n_frames;
   const uint32_t threads = 256;
   const uint64_t blocks = (warps * 32 + threads - 1) / threads;

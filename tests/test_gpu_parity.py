@@ -95,6 +95,20 @@ def test_hbma_vs_oracle_generic(gpu, oracle, L, bw, bh, R):
     assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
 
 
+@pytest.mark.parametrize("L,R", [(4, 8), (4, 16), (4, 24), (4, 32), (3, 4), (3, 8), (3, 12), (3, 16),
+                                 (5, 16), (5, 32), (2, 2), (2, 4), (2, 6), (2, 8)])
+@pytest.mark.parametrize("w,h", [(352, 208), (176, 80)])
+def test_hbma_tiled_path_vs_oracle(gpu, oracle, L, R, w, h):
+    """16x16 blocks with top-level range r = R >> (L-1) <= 4: the TMA-staged tiled kernel
+    (partial tiles on both axes, frame-border clamping, flat patch ties)."""
+    pw, ph = gpu.padded_dim(w, 16, L), gpu.padded_dim(h, 16, L)
+    seq = SyntheticSequence(w, h, 2, seed=L * 10 + R)
+    p0, p1 = oracle.y_pyramid(seq.frame(0), pw, ph, L), oracle.y_pyramid(seq.frame(1), pw, ph, L)
+    mv, mad = gpu.EstimateMotionHierarchical(p0, p1, L, pw, ph, R, 16, 16)
+    emv, emad = oracle.hbma(p0, p1, R)
+    assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+
+
 def test_hbma_flat_frames_tie_break(gpu, oracle):
     z = [np.zeros((64 >> l, 96 >> l), np.uint8) for l in range(4)]
     c = [np.full((64 >> l, 96 >> l), 9, np.uint8) for l in range(4)]
