@@ -299,12 +299,12 @@ def run_ours(a):
 
     def stage_pyr():
         for b in range(nb):
-            sess.run_stage(svc.STAGE_Y_PYRAMID, d_in.data_ptr() + b * B * fin, B)
+            sess.run_stage(svc.STAGE_PYR_DOWN, None, B)
         return nb
 
     def stage_pyr_hbma():  # HBMA right behind the pyramid build, as inside a step
         for b in range(nb):
-            sess.run_stage(svc.STAGE_Y_PYRAMID, d_in.data_ptr() + b * B * fin, B)
+            sess.run_stage(svc.STAGE_PYR_DOWN, None, B)
             sess.run_stage(svc.STAGE_HBMA, None, B, d_mv.data_ptr(), d_mad.data_ptr())
         return nb
 
@@ -314,18 +314,19 @@ def run_ours(a):
         ms_pyr = time_stage(stage_pyr)
         ms_hbma = max(time_stage(stage_pyr_hbma) - ms_pyr, 1e-6)
         P = sess.padded_w * sess.padded_h
-        dct_bytes = B * (fin + fst)                       # read BGR once, write records once
-        pyr_bytes = B * (fin + sum(P >> (2 * l) for l in range(a.levels)))
+        fused_y = (W == sess.padded_w)                     # K3 also writes the level-0 luma
+        dct_bytes = B * (fin + fst + (P if fused_y else 0))  # read BGR once, write records (+Y) once
+        pyr_bytes = B * sum(P >> (2 * l) for l in range(a.levels))  # read L0..L(n-2), write L1..L(n-1) ~ sum
         hbma_bytes = B * (2 * sum(P >> (2 * l) for l in range(a.levels)) + mvn * 12)
         stages = {
-            "dct_stream": {"ms_per_launch": ms_dct, "frames_per_launch": B,
-                           "algorithmic_bytes": dct_bytes, "gbs": dct_bytes / ms_dct / 1e6},
-            "y_pyramid": {"ms_per_launch_group": ms_pyr, "frames_per_launch": B,
-                          "algorithmic_bytes": pyr_bytes, "gbs": pyr_bytes / ms_pyr / 1e6},
+            "dct_stream_y": {"ms_per_launch": ms_dct, "frames_per_launch": B,
+                             "algorithmic_bytes": dct_bytes, "gbs": dct_bytes / ms_dct / 1e6},
+            "pyr_down": {"ms_per_launch_group": ms_pyr, "frames_per_launch": B,
+                         "algorithmic_bytes": pyr_bytes, "gbs": pyr_bytes / ms_pyr / 1e6},
             "hbma": {"ms_per_launch": ms_hbma, "frames_per_launch": B,
                      "algorithmic_bytes": hbma_bytes, "gbs": hbma_bytes / ms_hbma / 1e6},
         }
-        roofline = {"kernel": "dct8x8_kernel<stream> (K3: block DCT + stream records)",
+        roofline = {"kernel": "dct8x8_stream_kernel (K3: block DCT + stream records + level-0 luma)",
                     "bound": "hbm", "achieved": dct_bytes / ms_dct / 1e6, "peak": hbm_peak,
                     "unit": "GB/s", "frac": dct_bytes / ms_dct / 1e6 / hbm_peak, "traffic": None,
                     "peak_source": peak_src,

@@ -205,7 +205,9 @@ int svc_session_synchronize(svc_session* s);
  * Stage ids for svc_session_run_stage. */
 #define SVC_STAGE_Y_PYRAMID 1 /* K1: frames -> pyramid slots 1..n */
 #define SVC_STAGE_HBMA 2      /* K2: slots i,i+1 -> mv/mad of frame i */
-#define SVC_STAGE_DCT_STREAM 3 /* K3: frames -> stream records */
+#define SVC_STAGE_DCT_STREAM 3 /* K3: frames -> stream records (+ level-0 luma of slots 1..n
+                                  when the fused path applies: 8x8 blocks, W == padded W) */
+#define SVC_STAGE_PYR_DOWN 4   /* K1b: level 0 of slots 1..n -> levels 1.. */
 int svc_session_run_stage(svc_session* s, int stage,
                           const uint8_t* d_frames_bgr, uint32_t n_frames,
                           float* d_mv_xy, float* d_min_mad, uint8_t* d_stream);

@@ -75,7 +75,15 @@ struct DctParams {
   uint32_t mv_block_w, mv_block_h, mv_field_w, mv_field_h;
   float* scratch_planes;  // >= min(n, scratch_frames) x 3 x ph x pw, for the generic path
   uint32_t scratch_frames;
+  // optional fused level-0 luma output (only honoured when dct_can_fuse_y(p)):
+  // frame f of this launch -> pyramid slot y_first_slot + f
+  uint8_t* y_l0;  // slot array base + level-0 offset, or null
+  uint64_t y_slot_bytes;
+  uint32_t y_first_slot, y_pitch;
 };
+bool dct_can_fuse_y(const DctParams& p);
+// true when launch_dct(p) will need p.scratch_planes (generic transform / serializer path)
+bool dct_needs_scratch(const DctParams& p);
 cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* n_launches);
 // once per device (opt-in shared memory sizes etc.)
 cudaError_t prepare_dct_kernels();

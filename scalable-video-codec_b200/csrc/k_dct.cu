@@ -48,38 +48,48 @@ __device__ __forceinline__ void dct8(float& x0, float& x1, float& x2, float& x3,
   x7 = fmaf(SVC_D, d0, fmaf(-SVC_C, d1, fmaf(SVC_B, d2, -SVC_A * d3)));
 }
 
-// byte `b` of `w` -> exact float, via the 2^23 mantissa trick (PRMT + FADD)
-__device__ __forceinline__ float byte_to_float(uint32_t w, int b) {
-  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)b)) - 8388608.0f;
+// Row pass on "magic" floats.  A byte b placed in bits [15:8] of 0x47000000 is
+// the float 2^15 + b (one PRMT, no I2F).  Differences of two such values are
+// exact and offset free, sums are exact too (2^16 + b0 + b7, ...), so the only
+// place the offset survives is the DC term, where 8 * 2^15 is subtracted once:
+// 8 PRMT + 1 FADD per row instead of 8 PRMT + 8 FADD.
+__device__ __forceinline__ float byte_to_magic(uint32_t w, int b) {
+  return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7504u | ((uint32_t)b << 4)));
 }
 
-constexpr int kDctWarps = 4;          // warps per CTA
-constexpr int kRecWords8 = 193;       // 772-byte record = 1 + 3*64 words
-constexpr int kDctSmemStream = kDctWarps * 32 * kRecWords8 * 4;
+__device__ __forceinline__ void dct8_magic(float& x0, float& x1, float& x2, float& x3,
+                                           float& x4, float& x5, float& x6, float& x7) {
+  const float s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;   // 2^16 + ..
+  const float d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;   // exact
+  const float e0 = s0 + s3, e1 = s1 + s2, e2 = s0 - s3, e3 = s1 - s2;
+  x0 = SVC_C4 * ((e0 + e1) - 262144.0f);
+  x4 = SVC_C4 * (e0 - e1);
+  x2 = fmaf(SVC_B2, e2, SVC_B6 * e3);
+  x6 = fmaf(SVC_B6, e2, -SVC_B2 * e3);
+  x1 = fmaf(SVC_A, d0, fmaf(SVC_B, d1, fmaf(SVC_C, d2, SVC_D * d3)));
+  x3 = fmaf(SVC_B, d0, fmaf(-SVC_D, d1, fmaf(-SVC_A, d2, -SVC_C * d3)));
+  x5 = fmaf(SVC_C, d0, fmaf(-SVC_A, d1, fmaf(SVC_D, d2, SVC_B * d3)));
+  x7 = fmaf(SVC_D, d0, fmaf(-SVC_C, d1, fmaf(SVC_B, d2, -SVC_A * d3)));
+}
 
-enum { kModeStream = 0, kModePlanar = 1 };
+// 8x8 block of channel C out of 8 rows x 24 interleaved bytes -> 64 coefficients
+template <int C>
+__device__ __forceinline__ void dct_block(const uint32_t (&raw)[8][6], float (&v)[8][8]) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[r][j] = byte_to_magic(raw[r][(3 * j + C) >> 2], (3 * j + C) & 3);
+    dct8_magic(v[r][0], v[r][1], v[r][2], v[r][3], v[r][4], v[r][5], v[r][6], v[r][7]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    dct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+}
 
-// One lane = one 8x8 block (all three channels).  A warp covers 32 consecutive
-// blocks in serializer order (row-major over the nbx x nby block grid).
-template <int kMode>
-__global__ void __launch_bounds__(kDctWarps * 32)
-dct8x8_kernel(DctParams p, uint32_t nbx, uint32_t nby) {
-  extern __shared__ __align__(128) uint32_t smem[];
-  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-  const uint32_t per_frame = nbx * nby;
-  const uint32_t chunks_per_frame = (per_frame + 31u) / 32u;
-  const uint64_t unit = (uint64_t)blockIdx.x * kDctWarps + wib;
-  if (unit >= (uint64_t)chunks_per_frame * p.n_frames) return;
-  const uint32_t f = (uint32_t)(unit / chunks_per_frame);
-  const uint32_t n0 = (uint32_t)(unit % chunks_per_frame) * 32u;
-  const uint32_t n = n0 + lane;
-  const bool active = n < per_frame;
-  const uint32_t tbx = active ? n % nbx : 0u, tby = active ? n / nbx : 0u;
-  const uint32_t px = tbx * 8u, py = tby * 8u;
-
-  // ---- load 8 rows x 24 bytes (zero outside the unpadded frame) --------------
-  uint32_t raw[8][6];
-  const uint8_t* fr = p.bgr + (uint64_t)f * p.h * p.w * 3u;
+// 8 rows x 24 bytes of the lane's block; zero outside the unpadded frame
+// (cv::copyMakeBorder with zeros, libs/encoder.cpp:459-461).
+__device__ __forceinline__ void load_block_rows(const DctParams& p, const uint8_t* fr, bool active,
+                                                uint32_t px, uint32_t py, uint32_t (&raw)[8][6]) {
   const bool inside = active && (px + 8u <= p.w) && (py + 8u <= p.h);
   const bool vec_ok = ((p.w & 7u) == 0) && ((reinterpret_cast<uintptr_t>(p.bgr) & 7u) == 0);
   if (inside && vec_ok) {
@@ -104,70 +114,172 @@ dct8x8_kernel(DctParams p, uint32_t nbx, uint32_t nby) {
       }
     }
   }
+}
 
-  uint32_t* rec = smem + (wib * 32u + lane) * kRecWords8;  // stream mode staging
-  if (kMode == kModeStream) {
+constexpr int kRecWords8 = 193;  // 772-byte record = 1 + 3*64 words
+
+// ---- planar output (drop-in for Dct, libs/encoder.cpp:323-339) -------------------
+// One lane = one 8x8 block, three channels in turn, rows stored straight from
+// registers as 2 x 128-bit (32 lanes x 32 B = 1 KB contiguous per row).
+constexpr int kPlanarWarps = 4;
+__global__ void __launch_bounds__(kPlanarWarps * 32)
+dct8x8_planar_kernel(DctParams p, uint32_t nbx, uint32_t nby) {
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t per_frame = nbx * nby;
+  const uint32_t chunks_per_frame = (per_frame + 31u) / 32u;
+  const uint64_t unit = (uint64_t)blockIdx.x * kPlanarWarps + wib;
+  if (unit >= (uint64_t)chunks_per_frame * p.n_frames) return;
+  const uint32_t f = (uint32_t)(unit / chunks_per_frame);
+  const uint32_t n = (uint32_t)(unit % chunks_per_frame) * 32u + lane;
+  const bool active = n < per_frame;
+  const uint32_t tbx = active ? n % nbx : 0u, tby = active ? n / nbx : 0u;
+  const uint32_t px = tbx * 8u, py = tby * 8u;
+  uint32_t raw[8][6];
+  load_block_rows(p, p.bgr + (uint64_t)f * p.h * p.w * 3u, active, px, py, raw);
+  if (!active) return;
+  float v[8][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (c == 0) dct_block<0>(raw, v);
+    else if (c == 1) dct_block<1>(raw, v);
+    else dct_block<2>(raw, v);
+    float* pl = p.planes + (((uint64_t)f * 3u + c) * p.ph + py) * (uint64_t)p.pw + px;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float4* o = reinterpret_cast<float4*>(pl + (uint64_t)u * p.pw);
+      o[0] = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+      o[1] = make_float4(v[u][4], v[u][5], v[u][6], v[u][7]);
+    }
+  }
+}
+
+// ---- stream output (Dct + SerializeEncodedFrame) with fused Y extraction ------------
+// A CTA = 3 warps = one unit of 32 consecutive 8x8 blocks in serializer order;
+// warp c transforms channel c (B, G, R) of all 32 blocks, so the 772-byte
+// records are assembled by three warps into ONE shared staging buffer
+// (24.7 KB per 96 threads instead of per 32: three times the resident warps).
+// After a CTA barrier one elected lane hands the contiguous 32-record span to
+// the TMA engine (cp.async.bulk shared -> global); no scattered stores exist.
+// With kWithY the same pass also emits the level-0 luma rows of the blocks
+// (zero pad + BGR2YUV + extractChannel(0), libs/encoder.cpp:459-469): Y =
+// (1868 B + 9617 G + 4899 R + 8192) >> 14 as two 16x8-bit dot products (dp2a);
+// warp c takes block rows c, c+3, c+6.  Then K1 only has to downsample.
+struct YOut {
+  uint8_t* l0;          // slot array + level-0 offset (null: no Y output)
+  uint64_t slot_bytes;
+  uint32_t first_slot;  // frame f of this launch -> slot first_slot + f
+  uint32_t pitch;
+};
+
+__device__ __forceinline__ uint32_t luma_q14(uint32_t px /* B | G<<8 | R<<16 | x<<24 */) {
+  const uint32_t t = __dp2a_lo(1868u | (9617u << 16), px, 8192u);  // B, G
+  return __dp2a_hi(4899u, px, t) >> 14;                            // R (top byte x 0)
+}
+
+__device__ __forceinline__ uint2 luma_row8(const uint32_t (&w)[6]) {
+  const uint32_t y0 = luma_q14(w[0]);
+  const uint32_t y1 = luma_q14(__funnelshift_r(w[0], w[1], 24));
+  const uint32_t y2 = luma_q14(__funnelshift_r(w[1], w[2], 16));
+  const uint32_t y3 = luma_q14(w[2] >> 8);
+  const uint32_t y4 = luma_q14(w[3]);
+  const uint32_t y5 = luma_q14(__funnelshift_r(w[3], w[4], 24));
+  const uint32_t y6 = luma_q14(__funnelshift_r(w[4], w[5], 16));
+  const uint32_t y7 = luma_q14(w[5] >> 8);
+  return make_uint2(y0 | (y1 << 8) | (y2 << 16) | (y3 << 24),
+                    y4 | (y5 << 8) | (y6 << 16) | (y7 << 24));
+}
+
+template <bool kWithY>
+__global__ void __launch_bounds__(96)
+dct8x8_stream_kernel(const DctParams p, const uint32_t nbx, const uint32_t nby_stream,
+                     const uint32_t nby_total, const YOut yo) {
+  __shared__ __align__(128) uint32_t stage[32 * kRecWords8];
+  const uint32_t lane = threadIdx.x & 31u, c = threadIdx.x >> 5;  // c: channel of this warp
+  const uint32_t per_frame = nbx * nby_total;      // blocks visited (Y needs the padded rows)
+  const uint32_t per_stream = nbx * nby_stream;    // blocks that have a record
+  const uint32_t chunks_per_frame = (per_frame + 31u) / 32u;
+  const uint32_t f = blockIdx.x / chunks_per_frame;
+  const uint32_t n0 = (blockIdx.x % chunks_per_frame) * 32u;
+  const uint32_t n = n0 + lane;
+  const bool active = n < per_frame;
+  const uint32_t tbx = active ? n % nbx : 0u, tby = active ? n / nbx : 0u;
+  const uint32_t px = tbx * 8u, py = tby * 8u;
+
+  // 8 rows x 24 bytes; the host guarantees w % 8 == 0 and an 8-byte aligned base,
+  // so only whole rows can fall outside the frame (zero padding at the bottom)
+  uint32_t raw[8][7];
+  {
+    const uint8_t* q0 = p.bgr + (((uint64_t)f * p.h + py) * p.w + px) * 3u;
+    const uint64_t row_bytes = (uint64_t)p.w * 3u;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      uint2 a = make_uint2(0, 0), b = a, d = a;
+      if (active && py + r < p.h) {
+        const uint2* q = reinterpret_cast<const uint2*>(q0 + r * row_bytes);
+        a = __ldg(q); b = __ldg(q + 1); d = __ldg(q + 2);
+      }
+      raw[r][0] = a.x; raw[r][1] = a.y; raw[r][2] = b.x;
+      raw[r][3] = b.y; raw[r][4] = d.x; raw[r][5] = d.y; raw[r][6] = 0;
+    }
+  }
+
+  if (kWithY && active) {
+    uint8_t* yrow = yo.l0 + (uint64_t)(yo.first_slot + f) * yo.slot_bytes + (uint64_t)py * yo.pitch + px;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if ((uint32_t)(r % 3) == c) {
+        const uint32_t (&w)[7] = raw[r];
+        const uint32_t row6[6] = {w[0], w[1], w[2], w[3], w[4], w[5]};
+        *reinterpret_cast<uint2*>(yrow + (uint64_t)r * yo.pitch) = luma_row8(row6);
+      }
+  }
+  if (n0 >= per_stream) return;  // CTA-uniform: padded block rows carry no record
+
+  // Rotate every row by c bytes so this warp's channel sits at byte 3j: one code
+  // path (dct_block<0>) serves all three warps and the kernel stays I-cache sized.
+  const uint32_t sh = c * 8u;
+  uint32_t rot[8][6];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rot[r][k] = __funnelshift_r(raw[r][k], raw[r][k + 1], sh);
+  float v[8][8];
+  dct_block<0>(rot, v);
+
+  // word (lane*193 + const) -> bank (lane + const) % 32: conflict free
+  uint32_t* rec = stage + lane * kRecWords8;
+  if (c == 0) {
     uint32_t bt = 0;
-    if (p.block_types && active)
+    if (p.block_types && n < per_stream)
       bt = __ldg(p.block_types + (uint64_t)f * p.mv_field_w * p.mv_field_h +
                  (py / p.mv_block_h) * p.mv_field_w + px / p.mv_block_w);
     rec[0] = bt;
   }
+  uint32_t* recc = rec + 1 + c * 64;
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) recc[u * 8 + j] = __float_as_uint(v[u][j]);
 
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float v[8][8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[r][j] = byte_to_float(raw[r][(3 * j + c) >> 2], (3 * j + c) & 3);
-      dct8(v[r][0], v[r][1], v[r][2], v[r][3], v[r][4], v[r][5], v[r][6], v[r][7]);
+  const uint32_t n_act = min(32u, per_stream - n0);
+  const uint32_t bytes = n_act * kRecWords8 * 4u;
+  uint8_t* dst = p.stream + (uint64_t)f * p.frame_stream_bytes + (uint64_t)n0 * (kRecWords8 * 4u);
+  const bool bulk_ok = ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) && ((bytes & 15u) == 0);
+  if (bulk_ok) {
+    // generic-proxy smem writes -> visible to the async proxy, then one lane issues
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(stage);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(dst), "r"(s_addr), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the read
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      dct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
-
-    if (kMode == kModeStream) {
-      // word (lane*193 + const) -> bank (lane + const) % 32: conflict free
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rec[1 + c * 64 + u * 8 + j] = __float_as_uint(v[u][j]);
-    } else if (active) {
-      float* pl = p.planes + (((uint64_t)f * 3u + c) * p.ph + py) * (uint64_t)p.pw + px;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        float4* o = reinterpret_cast<float4*>(pl + (uint64_t)u * p.pw);
-        o[0] = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
-        o[1] = make_float4(v[u][4], v[u][5], v[u][6], v[u][7]);
-      }
-    }
-  }
-
-  if (kMode == kModeStream) {
-    const uint32_t n_act = min(32u, per_frame - n0);
-    const uint32_t bytes = n_act * kRecWords8 * 4u;
-    uint8_t* dst = p.stream + (uint64_t)f * p.frame_stream_bytes + (uint64_t)n0 * (kRecWords8 * 4u);
-    const uint32_t* src = smem + wib * 32u * kRecWords8;
-    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) && ((bytes & 15u) == 0);
-    if (bulk_ok) {
-      // make the generic-proxy smem writes visible to the async proxy, then one
-      // elected lane hands the whole span to the TMA engine.
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(src);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     :: "l"(dst), "r"(s_addr), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-      __syncwarp();
-    } else {
-      __syncwarp();
-      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-      for (uint32_t k = lane; k < bytes / 4u; k += 32u) d32[k] = src[k];
-    }
+  } else {
+    __syncthreads();
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+    for (uint32_t k = threadIdx.x; k < bytes / 4u; k += 96u) d32[k] = stage[k];
   }
 }
 
@@ -255,7 +367,7 @@ static cudaError_t planar_into(const DctParams& p, const uint8_t* bgr, uint32_t 
     q.bgr = bgr; q.n_frames = nf; q.planes = planes;
     const uint32_t nbx = p.pw / 8, nby = p.ph / 8;
     const uint64_t units = (uint64_t)((nbx * nby + 31) / 32) * nf;
-    dct8x8_kernel<kModePlanar><<<(uint32_t)((units + kDctWarps - 1) / kDctWarps), kDctWarps * 32, 0, st>>>(q, nbx, nby);
+    dct8x8_planar_kernel<<<(uint32_t)((units + kPlanarWarps - 1) / kPlanarWarps), kPlanarWarps * 32, 0, st>>>(q, nbx, nby);
     if (nl) *nl += 1;
     return cudaGetLastError();
   }
@@ -278,9 +390,28 @@ static cudaError_t planar_into(const DctParams& p, const uint8_t* bgr, uint32_t 
 }
 
 cudaError_t prepare_dct_kernels() {
-  return cudaFuncSetAttribute(dct8x8_kernel<kModeStream>,
-                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              kDctSmemStream);
+  // the staging buffers want the large shared-memory carve-out (9 CTAs x 24.7 KB)
+  cudaError_t e = cudaFuncSetAttribute(dct8x8_stream_kernel<true>,
+                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dct8x8_stream_kernel<false>,
+                              cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+
+// the fused stream kernel: 8x8 blocks, no horizontal padding (so the serializer's
+// unpadded row stride equals the plane stride), 8-byte aligned 24-byte block rows
+static bool dct_fast_stream_ok(const DctParams& p) {
+  return p.tbw == 8 && p.tbh == 8 && p.w == p.pw && (p.w % 8u) == 0 &&
+         (reinterpret_cast<uintptr_t>(p.bgr) & 7u) == 0;
+}
+
+bool dct_needs_scratch(const DctParams& p) {
+  const bool fast8 = (p.tbw == 8 && p.tbh == 8);
+  return (p.planes && !fast8) || (p.stream && !dct_fast_stream_ok(p));
+}
+
+bool dct_can_fuse_y(const DctParams& p) {
+  return p.stream && dct_fast_stream_ok(p) && (p.ph % 8u) == 0;
 }
 
 cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* nl) {
@@ -304,10 +435,15 @@ cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* nl) {
     }
   }
   if (p.stream) {
-    if (fast8 && p.w == p.pw) {
+    if (dct_fast_stream_ok(p)) {
       const uint32_t nbx = p.w / 8, nby = (p.h + 7) / 8;
-      const uint64_t units = (uint64_t)((nbx * nby + 31) / 32) * p.n_frames;
-      dct8x8_kernel<kModeStream><<<(uint32_t)((units + kDctWarps - 1) / kDctWarps), kDctWarps * 32, kDctSmemStream, st>>>(p, nbx, nby);
+      const bool with_y = p.y_l0 != nullptr;
+      const uint32_t nby_total = with_y ? p.ph / 8 : nby;
+      const uint64_t units = (uint64_t)((nbx * nby_total + 31) / 32) * p.n_frames;
+      if (units > 0x7fffffffull) return cudaErrorInvalidValue;
+      YOut yo{p.y_l0, p.y_slot_bytes, p.y_first_slot, p.y_pitch};
+      if (with_y) dct8x8_stream_kernel<true><<<(uint32_t)units, 96, 0, st>>>(p, nbx, nby, nby_total, yo);
+      else dct8x8_stream_kernel<false><<<(uint32_t)units, 96, 0, st>>>(p, nbx, nby, nby_total, yo);
       if (nl) *nl += 1;
       e = cudaGetLastError();
       if (e != cudaSuccess) return e;

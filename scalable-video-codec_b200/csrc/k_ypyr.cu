@@ -85,56 +85,109 @@ cudaError_t launch_bgr_to_y(const uint8_t* d_bgr, uint32_t w, uint32_t h,
 }
 
 // ---------------------------------------------------------------------------
-// pyrDown.  One thread produces 4 output pixels of one row: it needs source
-// columns 2*x0-2 .. 2*x0+8 of 5 source rows.  Interior threads fetch them as
-// four aligned words per row; threads at the left/right border take the
-// byte path with cv::borderInterpolate(BORDER_REFLECT_101) semantics.
+// pyrDown (one level per launch), shared-memory tiled.
+//
+// A CTA of 128 threads produces a 128 x 32 tile of the destination level.  The
+// (2*128+32) x (2*32+3) source region is staged in shared memory once with
+// cv::borderInterpolate(BORDER_REFLECT_101) applied at load time (128-bit loads
+// for chunks inside the image, byte loads on the borders), so the arithmetic
+// below never sees a border.  Each thread then owns 4 output columns x 8 output
+// rows: it walks the 19 source rows of its strip once, forms the four
+// horizontal [1 4 6 4 1] sums of a row with packed-byte dot products (dp4a)
+// and scatters them into the (at most three) live vertical accumulators.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int reflect101(int p, int len) {
   if (len == 1) return 0;
-  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+  // one fold covers every coordinate a tile can ask for unless the level is tiny
+  if (p < 0) p = -p; else if (p >= len) p = 2 * len - 2 - p;
+  if (p < 0 || p >= len) {
+    const int period = 2 * len - 2;
+    p = p % period;
+    if (p < 0) p += period;
+    if (p >= len) p = period - p;
+  }
   return p;
 }
 
+constexpr int kPdTileW = 128, kPdTileH = 32;            // destination tile
+constexpr int kPdSrcW = 2 * kPdTileW + 32;               // 288: cols 2*x0-16 .. 2*x0+271
+constexpr int kPdSrcH = 2 * kPdTileH + 3;                // 67:  rows 2*y0-2 .. 2*y0+64
+
 __global__ void __launch_bounds__(128)
-pyr_down_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes,
-                uint32_t first_slot, uint64_t src_off, uint32_t sw, uint32_t sh,
-                uint32_t spitch, uint64_t dst_off, uint32_t dw, uint32_t dh,
-                uint32_t dpitch) {
-  const uint32_t x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-  const uint32_t oy = blockIdx.y;
-  if (x0 >= dw) return;
+pyr_down_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t first_slot,
+                uint64_t src_off, uint32_t sw, uint32_t sh, uint32_t spitch,
+                uint64_t dst_off, uint32_t dw, uint32_t dh, uint32_t dpitch) {
+  __shared__ __align__(16) uint8_t tile[kPdSrcH * kPdSrcW];
   uint8_t* slot = pyr + (uint64_t)(first_slot + blockIdx.z) * slot_bytes;
   const uint8_t* src = slot + src_off;
-  const bool interior = (x0 >= 2u) && (2u * x0 + 12u <= sw);
-  int acc[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const int wv = (k == 0 || k == 4) ? 1 : ((k == 2) ? 6 : 4);
-    const int sy = reflect101((int)oy * 2 + k - 2, (int)sh);
-    const uint8_t* row = src + (uint64_t)sy * spitch;
-    int p[11];
-    if (interior) {
-      const uint32_t* q = reinterpret_cast<const uint32_t*>(row + 2u * x0 - 4u);
-      const uint32_t a = q[0], b = q[1], c = q[2], d = q[3];
-      p[0] = (a >> 16) & 0xff;  p[1] = a >> 24;
-      p[2] = b & 0xff;  p[3] = (b >> 8) & 0xff;  p[4] = (b >> 16) & 0xff;  p[5] = b >> 24;
-      p[6] = c & 0xff;  p[7] = (c >> 8) & 0xff;  p[8] = (c >> 16) & 0xff;  p[9] = c >> 24;
-      p[10] = d & 0xff;
+  const int x0t = blockIdx.x * kPdTileW, y0t = blockIdx.y * kPdTileH;
+  const int sx0 = 2 * x0t - 16, sy0 = 2 * y0t - 2;  // source coords of tile[0][0] (16-byte aligned)
+
+  // ---- stage the source region (reflect at load) ----------------------------
+  // only what this tile's outputs read: source cols <= 2*xe, rows <= 2*ye
+  const int xe = min(x0t + kPdTileW, (int)dw), ye = min(y0t + kPdTileH, (int)dh);
+  constexpr int kChunks = kPdSrcW / 16;  // 18 x 16-byte chunks per row
+  const int n_rows = 2 * (ye - y0t) + 3;
+  for (int i = threadIdx.x; i < n_rows * kChunks; i += 128) {
+    const int row = i / kChunks, ch = i - row * kChunks;
+    const int cx = sx0 + ch * 16;
+    if (cx > 2 * xe) continue;
+    const int sy = reflect101(sy0 + row, (int)sh);
+    const uint8_t* srow = src + (uint64_t)sy * spitch;
+    uint4 v;
+    if (cx >= 0 && cx + 16 <= (int)sw) {
+      v = __ldg(reinterpret_cast<const uint4*>(srow + cx));  // spitch % 128 == 0, cx % 16 == 0
     } else {
+      uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int j = 0; j < 11; ++j)
-        p[j] = row[reflect101((int)(2u * x0) - 2 + j, (int)sw)];
+      for (int k = 0; k < 16; ++k)
+        w[k >> 2] |= (uint32_t)srow[reflect101(cx + k, (int)sw)] << (8 * (k & 3));
+      v = make_uint4(w[0], w[1], w[2], w[3]);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      acc[i] += wv * (p[2 * i] + 4 * p[2 * i + 1] + 6 * p[2 * i + 2] +
-                      4 * p[2 * i + 3] + p[2 * i + 4]);
+    *reinterpret_cast<uint4*>(tile + row * kPdSrcW + ch * 16) = v;
   }
-  uint32_t out = 0;
+  __syncthreads();
+
+  // ---- 4 columns x 8 rows per thread ------------------------------------------
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ox = x0t + 4 * tx, oy = y0t + 8 * ty;
+  if (ox >= (int)dw || oy >= (int)dh) return;
+  // source columns 2*ox-2 .. 2*ox+8 live at tile columns 8*tx+14 .. 8*tx+24
+  const uint8_t* tcol = tile + (16 * ty) * kPdSrcW + 8 * tx + 8;
+  // vertical accumulators, two 16-bit columns per register: a [1 4 6 4 1]^2 sum is at
+  // most 255 * 256 = 65280 (+128 rounding) < 2^16, so the halves never carry over
+  uint32_t acc[8][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) out |= (uint32_t)((acc[i] + 128) >> 8) << (8 * i);
-  *reinterpret_cast<uint32_t*>(slot + dst_off + (uint64_t)oy * dpitch + x0) = out;
+  for (int y = 0; y < 8; ++y) acc[y][0] = acc[y][1] = 0;
+#pragma unroll
+  for (int r = 0; r < 19; ++r) {
+    const uint2 a = *reinterpret_cast<const uint2*>(tcol + r * kPdSrcW);        // tile cols 8tx+8 ..
+    const uint2 b = *reinterpret_cast<const uint2*>(tcol + r * kPdSrcW + 8);    // tile cols 8tx+16 ..
+    const uint32_t c = *reinterpret_cast<const uint32_t*>(tcol + r * kPdSrcW + 16);
+    // p[j] = tile col 8tx+14+j.  h[i] = dp4a(p[2i..2i+3], {1,4,6,4}) + p[2i+4]
+    const uint32_t h0 = __dp4a(__funnelshift_r(a.y, b.x, 16), 0x04060401u, (b.x >> 16) & 0xffu);
+    const uint32_t h1 = __dp4a(b.x, 0x04060401u, b.y & 0xffu);
+    const uint32_t h2 = __dp4a(__funnelshift_r(b.x, b.y, 16), 0x04060401u, (b.y >> 16) & 0xffu);
+    const uint32_t h3 = __dp4a(b.y, 0x04060401u, c & 0xffu);
+    const uint32_t hp0 = h1 * 65536u + h0, hp1 = h3 * 65536u + h2;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      const int k = r - 2 * y;  // vertical tap index for output row y
+      if (k >= 0 && k <= 4) {
+        const uint32_t wv = (k == 0 || k == 4) ? 1u : ((k == 2) ? 6u : 4u);
+        acc[y][0] += wv * hp0;
+        acc[y][1] += wv * hp1;
+      }
+    }
+  }
+  uint8_t* drow = slot + dst_off + (uint64_t)oy * dpitch + ox;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {
+    if (oy + y < (int)dh) {
+      const uint32_t t0 = (acc[y][0] + 0x00800080u) >> 8, t1 = (acc[y][1] + 0x00800080u) >> 8;
+      *reinterpret_cast<uint32_t*>(drow + (uint64_t)y * dpitch) = __byte_perm(t0, t1, 0x6420);
+    }
+  }
 }
 
 cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
@@ -144,7 +197,7 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
   const uint32_t l = src_level;
   const uint32_t dw = lay.w[l + 1], dh = lay.h[l + 1];
   dim3 block(128);
-  dim3 grid(((dw + 3) / 4 + 127) / 128, dh, n_frames);
+  dim3 grid((dw + kPdTileW - 1) / kPdTileW, (dh + kPdTileH - 1) / kPdTileH, n_frames);
   pyr_down_kernel<<<grid, block, 0, st>>>(d_pyr, lay.slot_bytes, first_slot,
                                           lay.off[l], lay.w[l], lay.h[l],
                                           lay.pitch[l], lay.off[l + 1], dw, dh,

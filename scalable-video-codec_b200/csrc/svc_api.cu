@@ -419,8 +419,45 @@ int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, flo
   const uint32_t n_enc = s->have_prev ? m : m - 1;
   const uint32_t mvn = s->info.mv_field_w * s->info.mv_field_h;
   int nl = 0;
-  CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, s->d_pyr, s->lay, first_slot, m, s->stream));
-  nl += 1;
+  DctParams dp{};
+  if (n_enc && d_stream) {
+    dp.bgr = d_frames + (size_t)(m - n_enc) * s->info.frame_in_bytes;
+    dp.w = s->cfg.frame_w; dp.h = s->cfg.frame_h;
+    dp.pw = s->info.padded_w; dp.ph = s->info.padded_h;
+    dp.tbw = s->cfg.transform_block_w; dp.tbh = s->cfg.transform_block_h;
+    dp.n_frames = n_enc;
+    dp.stream = d_stream;
+    dp.frame_stream_bytes = s->info.frame_stream_bytes;
+    dp.block_types = d_bt;
+    dp.mv_block_w = s->cfg.mv_block_w; dp.mv_block_h = s->cfg.mv_block_h;
+    dp.mv_field_w = s->info.mv_field_w; dp.mv_field_h = s->info.mv_field_h;
+    dp.scratch_planes = s->d_scratch;
+    dp.scratch_frames = s->scratch_frames;
+  }
+  if (n_enc && d_stream && dct_needs_scratch(dp) && !s->d_scratch) {
+    // e.g. a caller-supplied frame pointer that is not 8-byte aligned
+    s->scratch_frames = std::min<uint32_t>(s->info.max_batch, 4);
+    CU(cudaMalloc(&s->d_scratch, (size_t)s->scratch_frames * 6 * dp.pw * dp.ph * sizeof(float)));
+    dp.scratch_planes = s->d_scratch;
+    dp.scratch_frames = s->scratch_frames;
+  }
+  const bool fuse_y = n_enc && d_stream && dct_can_fuse_y(dp);
+  if (fuse_y) {
+    // K3 also emits the level-0 luma of every encoded frame (slots 1..n_enc); a
+    // tracked-only first frame (slot 0) still needs the stand-alone conversion.
+    if (!s->have_prev) {
+      CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, s->d_pyr, s->lay, 0, 1, s->stream));
+      nl += 1;
+    }
+    dp.y_l0 = s->d_pyr + s->lay.off[0];
+    dp.y_slot_bytes = s->lay.slot_bytes;
+    dp.y_first_slot = 1;
+    dp.y_pitch = s->lay.pitch[0];
+    CU(launch_dct(dp, s->stream, &nl));
+  } else {
+    CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, s->d_pyr, s->lay, first_slot, m, s->stream));
+    nl += 1;
+  }
   for (uint32_t l = 0; l + 1 < s->lay.levels; ++l) {
     CU(launch_pyr_down(s->d_pyr, s->lay, l, first_slot, m, s->stream));
     nl += 1;
@@ -439,22 +476,7 @@ int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, flo
     p.n_frames = n_enc;
     CU(launch_hbma(p, s->stream, &nl));
   }
-  if (n_enc && d_stream) {
-    DctParams p{};
-    p.bgr = d_frames + (size_t)(m - n_enc) * s->info.frame_in_bytes;
-    p.w = s->cfg.frame_w; p.h = s->cfg.frame_h;
-    p.pw = s->info.padded_w; p.ph = s->info.padded_h;
-    p.tbw = s->cfg.transform_block_w; p.tbh = s->cfg.transform_block_h;
-    p.n_frames = n_enc;
-    p.stream = d_stream;
-    p.frame_stream_bytes = s->info.frame_stream_bytes;
-    p.block_types = d_bt;
-    p.mv_block_w = s->cfg.mv_block_w; p.mv_block_h = s->cfg.mv_block_h;
-    p.mv_field_w = s->info.mv_field_w; p.mv_field_h = s->info.mv_field_h;
-    p.scratch_planes = s->d_scratch;
-    p.scratch_frames = s->scratch_frames;
-    CU(launch_dct(p, s->stream, &nl));
-  }
+  if (n_enc && d_stream && !fuse_y) CU(launch_dct(dp, s->stream, &nl));
   // keep the last frame's pyramid as the next tracked frame (libs/encoder.cpp:661-663)
   const uint32_t last = first_slot + m - 1;
   if (last != 0) {
@@ -743,7 +765,20 @@ int svc_session_run_stage(svc_session* s, int stage, const uint8_t* d_frames, ui
       p.mv_field_w = s->info.mv_field_w; p.mv_field_h = s->info.mv_field_h;
       p.scratch_planes = s->d_scratch;
       p.scratch_frames = s->scratch_frames;
+      if (dct_can_fuse_y(p)) {  // as inside a step: level-0 luma of slots 1..n rides along
+        p.y_l0 = s->d_pyr + s->lay.off[0];
+        p.y_slot_bytes = s->lay.slot_bytes;
+        p.y_first_slot = 1;
+        p.y_pitch = s->lay.pitch[0];
+      }
       CU(launch_dct(p, s->stream, &nl));
+      break;
+    }
+    case SVC_STAGE_PYR_DOWN: {
+      for (uint32_t l = 0; l + 1 < s->lay.levels; ++l) {
+        CU(launch_pyr_down(s->d_pyr, s->lay, l, 1, n_frames, s->stream));
+        nl += 1;
+      }
       break;
     }
     default:

@@ -12,7 +12,7 @@ from .binding import (  # noqa: F401
     write_header, EstimateMotionHierarchical, EstimateMotionHierarchical16x16Sse2,
     EstimateMotionExhaustiveSearch, y_pyramid, dct_planar, encode_frame_stream,
     patch_block_types, Session, SessionConfig, PinnedBuffer, DeviceBuffer,
-    STAGE_Y_PYRAMID, STAGE_HBMA, STAGE_DCT_STREAM,
+    STAGE_Y_PYRAMID, STAGE_HBMA, STAGE_DCT_STREAM, STAGE_PYR_DOWN,
 )
 from .shard import shard_frame_ranges, gather_streams  # noqa: F401
 from .synth import SyntheticSequence  # noqa: F401

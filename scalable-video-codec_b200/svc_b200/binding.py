@@ -17,7 +17,7 @@ _u8p = C.POINTER(C.c_uint8)
 _f32p = C.POINTER(C.c_float)
 _u32p = C.POINTER(C.c_uint32)
 
-STAGE_Y_PYRAMID, STAGE_HBMA, STAGE_DCT_STREAM = 1, 2, 3
+STAGE_Y_PYRAMID, STAGE_HBMA, STAGE_DCT_STREAM, STAGE_PYR_DOWN = 1, 2, 3, 4
 
 
 class SvcError(RuntimeError):
