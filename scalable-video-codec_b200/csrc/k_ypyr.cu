@@ -10,6 +10,8 @@
 //                                                      (sum + 128) >> 8,
 //                                                      BORDER_REFLECT_101
 // All arithmetic is integer and bit-exact with OpenCV's 8-bit paths.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace svc {
@@ -109,58 +111,72 @@ __device__ __forceinline__ int reflect101(int p, int len) {
   return p;
 }
 
-constexpr int kPdTileW = 128, kPdTileH = 32;            // destination tile
-constexpr int kPdSrcW = 2 * kPdTileW + 32;               // 288: cols 2*x0-16 .. 2*x0+271
-constexpr int kPdSrcH = 2 * kPdTileH + 3;                // 67:  rows 2*y0-2 .. 2*y0+64
+// One fold + clamp: exact for every coordinate a valid output reads (overshoot <= 2)
+// once the level is at least 4 wide/high; smaller levels take pyr_down_small_kernel.
+__device__ __forceinline__ int reflect101_near(int p, int len) {
+  p = p < 0 ? -p : (p >= len ? 2 * len - 2 - p : p);
+  return min(max(p, 0), len - 1);
+}
 
+constexpr int kPdTileW = 128;                             // destination tile width
+constexpr int kPdSrcW = 2 * kPdTileW + 32;                 // 288: cols 2*x0-16 .. 2*x0+271
+constexpr int kPdChunks = kPdSrcW / 16;                    // 18 x 16-byte chunks per row
+
+// kRpt = destination rows per thread (tile height = 4 * kRpt).  8 for the big
+// level-0 -> 1 launch; 2 for the small upper levels, where the launch is bound
+// by the latency of one CTA rather than by throughput.
+template <int kRpt>
 __global__ void __launch_bounds__(128)
 pyr_down_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t first_slot,
                 uint64_t src_off, uint32_t sw, uint32_t sh, uint32_t spitch,
                 uint64_t dst_off, uint32_t dw, uint32_t dh, uint32_t dpitch) {
-  __shared__ __align__(16) uint8_t tile[kPdSrcH * kPdSrcW];
+  constexpr int kTileH = 4 * kRpt;
+  constexpr int kSrcH = 2 * kTileH + 3;
+  constexpr int kRows = 2 * kRpt + 3;  // source rows per thread
+  __shared__ __align__(16) uint8_t tile[kSrcH * kPdSrcW];
   uint8_t* slot = pyr + (uint64_t)(first_slot + blockIdx.z) * slot_bytes;
   const uint8_t* src = slot + src_off;
-  const int x0t = blockIdx.x * kPdTileW, y0t = blockIdx.y * kPdTileH;
+  const int x0t = blockIdx.x * kPdTileW, y0t = blockIdx.y * kTileH;
   const int sx0 = 2 * x0t - 16, sy0 = 2 * y0t - 2;  // source coords of tile[0][0] (16-byte aligned)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 
-  // ---- stage the source region (reflect at load) ----------------------------
+  // ---- stage the source region (reflect at load): warp = row, lane = 16-byte chunk;
   // only what this tile's outputs read: source cols <= 2*xe, rows <= 2*ye
-  const int xe = min(x0t + kPdTileW, (int)dw), ye = min(y0t + kPdTileH, (int)dh);
-  constexpr int kChunks = kPdSrcW / 16;  // 18 x 16-byte chunks per row
-  const int n_rows = 2 * (ye - y0t) + 3;
-  for (int i = threadIdx.x; i < n_rows * kChunks; i += 128) {
-    const int row = i / kChunks, ch = i - row * kChunks;
-    const int cx = sx0 + ch * 16;
-    if (cx > 2 * xe) continue;
-    const int sy = reflect101(sy0 + row, (int)sh);
-    const uint8_t* srow = src + (uint64_t)sy * spitch;
-    uint4 v;
-    if (cx >= 0 && cx + 16 <= (int)sw) {
-      v = __ldg(reinterpret_cast<const uint4*>(srow + cx));  // spitch % 128 == 0, cx % 16 == 0
-    } else {
-      uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int k = 0; k < 16; ++k)
-        w[k >> 2] |= (uint32_t)srow[reflect101(cx + k, (int)sw)] << (8 * (k & 3));
-      v = make_uint4(w[0], w[1], w[2], w[3]);
+  {
+    const int xe = min(x0t + kPdTileW, (int)dw), ye = min(y0t + kTileH, (int)dh);
+    const int n_rows = 2 * (ye - y0t) + 3;
+    const int cx = sx0 + tx * 16;
+    const int need_lo = 2 * x0t - 2, need_hi = 2 * xe;  // source columns the outputs read
+    const bool lane_on = tx < kPdChunks && cx <= need_hi && cx + 15 >= need_lo;
+    const bool lane_fast = cx >= 0 && cx + 16 <= (int)sw;
+    const int k_lo = max(need_lo - cx, 0), k_hi = min(need_hi - cx, 15);  // border chunk: bytes to fill
+    for (int row = ty; row < n_rows; row += 4) {
+      const uint8_t* srow = src + (uint64_t)reflect101_near(sy0 + row, (int)sh) * spitch;
+      uint8_t* trow = tile + row * kPdSrcW + tx * 16;
+      if (lane_on) {
+        if (lane_fast) {
+          *reinterpret_cast<uint4*>(trow) = __ldg(reinterpret_cast<const uint4*>(srow + cx));
+        } else {
+#pragma unroll 1
+          for (int k = k_lo; k <= k_hi; ++k) trow[k] = srow[reflect101_near(cx + k, (int)sw)];
+        }
+      }
     }
-    *reinterpret_cast<uint4*>(tile + row * kPdSrcW + ch * 16) = v;
   }
   __syncthreads();
 
-  // ---- 4 columns x 8 rows per thread ------------------------------------------
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int ox = x0t + 4 * tx, oy = y0t + 8 * ty;
+  // ---- 4 columns x kRpt rows per thread ------------------------------------------
+  const int ox = x0t + 4 * tx, oy = y0t + kRpt * ty;
   if (ox >= (int)dw || oy >= (int)dh) return;
   // source columns 2*ox-2 .. 2*ox+8 live at tile columns 8*tx+14 .. 8*tx+24
-  const uint8_t* tcol = tile + (16 * ty) * kPdSrcW + 8 * tx + 8;
+  const uint8_t* tcol = tile + (2 * kRpt * ty) * kPdSrcW + 8 * tx + 8;
   // vertical accumulators, two 16-bit columns per register: a [1 4 6 4 1]^2 sum is at
   // most 255 * 256 = 65280 (+128 rounding) < 2^16, so the halves never carry over
-  uint32_t acc[8][2];
+  uint32_t acc[kRpt][2];
 #pragma unroll
-  for (int y = 0; y < 8; ++y) acc[y][0] = acc[y][1] = 0;
+  for (int y = 0; y < kRpt; ++y) acc[y][0] = acc[y][1] = 0;
 #pragma unroll
-  for (int r = 0; r < 19; ++r) {
+  for (int r = 0; r < kRows; ++r) {
     const uint2 a = *reinterpret_cast<const uint2*>(tcol + r * kPdSrcW);        // tile cols 8tx+8 ..
     const uint2 b = *reinterpret_cast<const uint2*>(tcol + r * kPdSrcW + 8);    // tile cols 8tx+16 ..
     const uint32_t c = *reinterpret_cast<const uint32_t*>(tcol + r * kPdSrcW + 16);
@@ -171,7 +187,7 @@ pyr_down_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t first_s
     const uint32_t h3 = __dp4a(b.y, 0x04060401u, c & 0xffu);
     const uint32_t hp0 = h1 * 65536u + h0, hp1 = h3 * 65536u + h2;
 #pragma unroll
-    for (int y = 0; y < 8; ++y) {
+    for (int y = 0; y < kRpt; ++y) {
       const int k = r - 2 * y;  // vertical tap index for output row y
       if (k >= 0 && k <= 4) {
         const uint32_t wv = (k == 0 || k == 4) ? 1u : ((k == 2) ? 6u : 4u);
@@ -182,12 +198,37 @@ pyr_down_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t first_s
   }
   uint8_t* drow = slot + dst_off + (uint64_t)oy * dpitch + ox;
 #pragma unroll
-  for (int y = 0; y < 8; ++y) {
+  for (int y = 0; y < kRpt; ++y) {
     if (oy + y < (int)dh) {
       const uint32_t t0 = (acc[y][0] + 0x00800080u) >> 8, t1 = (acc[y][1] + 0x00800080u) >> 8;
       *reinterpret_cast<uint32_t*>(drow + (uint64_t)y * dpitch) = __byte_perm(t0, t1, 0x6420);
     }
   }
+}
+
+// Levels narrower or lower than 4 pixels (tiny frames): one thread per output
+// pixel with the full cv::borderInterpolate reflection.
+__global__ void __launch_bounds__(128)
+pyr_down_small_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t first_slot,
+                      uint64_t src_off, uint32_t sw, uint32_t sh, uint32_t spitch,
+                      uint64_t dst_off, uint32_t dw, uint32_t dh, uint32_t dpitch) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dw * dh) return;
+  const int ox = (int)(i % dw), oy = (int)(i / dw);
+  uint8_t* slot = pyr + (uint64_t)(first_slot + blockIdx.z) * slot_bytes;
+  const uint8_t* src = slot + src_off;
+  int acc = 0;
+  for (int k = 0; k < 5; ++k) {
+    const int wv = (k == 0 || k == 4) ? 1 : ((k == 2) ? 6 : 4);
+    const uint8_t* row = src + (uint64_t)reflect101(2 * oy + k - 2, (int)sh) * spitch;
+    int hsum = 0;
+    for (int j = 0; j < 5; ++j) {
+      const int wh = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
+      hsum += wh * row[reflect101(2 * ox + j - 2, (int)sw)];
+    }
+    acc += wv * hsum;
+  }
+  slot[dst_off + (uint64_t)oy * dpitch + ox] = (uint8_t)((acc + 128) >> 8);
 }
 
 cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
@@ -197,11 +238,25 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
   const uint32_t l = src_level;
   const uint32_t dw = lay.w[l + 1], dh = lay.h[l + 1];
   dim3 block(128);
-  dim3 grid((dw + kPdTileW - 1) / kPdTileW, (dh + kPdTileH - 1) / kPdTileH, n_frames);
-  pyr_down_kernel<<<grid, block, 0, st>>>(d_pyr, lay.slot_bytes, first_slot,
-                                          lay.off[l], lay.w[l], lay.h[l],
-                                          lay.pitch[l], lay.off[l + 1], dw, dh,
-                                          lay.pitch[l + 1]);
+  if (lay.w[l] < 4 || lay.h[l] < 4) {
+    pyr_down_small_kernel<<<dim3((dw * dh + 127) / 128, 1, n_frames), block, 0, st>>>(
+        d_pyr, lay.slot_bytes, first_slot, lay.off[l], lay.w[l], lay.h[l], lay.pitch[l], lay.off[l + 1],
+        dw, dh, lay.pitch[l + 1]);
+    return cudaGetLastError();
+  }
+  static const char* env_thr = getenv("SVC_PYR_BIG_MPIX");  // tuning hook
+  const uint64_t thr = env_thr ? (uint64_t)atoll(env_thr) << 20 : (8ull << 20);
+  const bool big = (uint64_t)dw * dh * n_frames >= thr;
+  const uint32_t tile_h = big ? 32 : 8;
+  dim3 grid((dw + kPdTileW - 1) / kPdTileW, (dh + tile_h - 1) / tile_h, n_frames);
+  if (big)
+    pyr_down_kernel<8><<<grid, block, 0, st>>>(d_pyr, lay.slot_bytes, first_slot, lay.off[l], lay.w[l],
+                                               lay.h[l], lay.pitch[l], lay.off[l + 1], dw, dh,
+                                               lay.pitch[l + 1]);
+  else
+    pyr_down_kernel<2><<<grid, block, 0, st>>>(d_pyr, lay.slot_bytes, first_slot, lay.off[l], lay.w[l],
+                                               lay.h[l], lay.pitch[l], lay.off[l + 1], dw, dh,
+                                               lay.pitch[l + 1]);
   return cudaGetLastError();
 }
 
