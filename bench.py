@@ -326,9 +326,16 @@ def run_ours(a):
             "hbma": {"ms_per_launch": ms_hbma, "frames_per_launch": B,
                      "algorithmic_bytes": hbma_bytes, "gbs": hbma_bytes / ms_hbma / 1e6},
         }
+        traffic = None
+        try:  # DRAM bytes of this kernel from the committed ncu --set full capture (same geometry only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["dct8x8_stream_kernel"]
+            if (W, H) == (1920, 1080) and fused_y:
+                traffic = tj["dram_bytes_per_launch"] * B / tj["frames_per_launch"]
+        except Exception:
+            pass
         roofline = {"kernel": "dct8x8_stream_kernel (K3: block DCT + stream records + level-0 luma)",
                     "bound": "hbm", "achieved": dct_bytes / ms_dct / 1e6, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": dct_bytes / ms_dct / 1e6 / hbm_peak, "traffic": None,
+                    "unit": "GB/s", "frac": dct_bytes / ms_dct / 1e6 / hbm_peak, "traffic": traffic,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dct_bytes}
     else:

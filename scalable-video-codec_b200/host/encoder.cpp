@@ -1,0 +1,135 @@
+// encoder.cpp -- see encoder.hpp.  Per-batch flow (one GPU):
+//   pop up to max_batch frames -> svc_session_encode (H2D | K3+K1 | K2 | D2H)
+//   -> per encoded frame: block-type callback on the motion field, patch the
+//   4-byte block types into the GPU-written records, push the bytes.
+#include "encoder.hpp"
+
+#include <cstring>
+
+#include "../../include/svc_b200.h"
+
+namespace svc {
+
+Status Validate(const EncoderConfig& cfg) {
+  // messages as in libs/encoder.cpp:62-142
+  if (cfg.mv_block_w < 1) return {ErrorCode::kInvalidParameter, "invalid mv block width: must be > 0"};
+  if (cfg.mv_block_h < 1) return {ErrorCode::kInvalidParameter, "invalid mv block height: must be > 0"};
+  if (cfg.pyr_lvl_count < 1)
+    return {ErrorCode::kInvalidParameter, "invalid pyramid level count: must be > 0"};
+  if (cfg.pyr_lvl_count > SVC_MAX_LEVELS)
+    return {ErrorCode::kInvalidParameter, "invalid pyramid level count: must be <= 8"};
+  if (cfg.mv_search_range / (1u << (cfg.pyr_lvl_count - 1)) == 0)
+    return {ErrorCode::kInvalidParameter,
+            "invalid mv search and pyramid level count: the quotient from dividing the mv search "
+            "range by the pyramid level reduction factor must be > 0"};
+  if (cfg.transform_block_w < 1)
+    return {ErrorCode::kInvalidParameter, "invalid transform block width: must be > 0"};
+  if (cfg.transform_block_h < 1)
+    return {ErrorCode::kInvalidParameter, "invalid transform block height: must be > 0"};
+  if (cfg.transform_block_w > cfg.mv_block_w)
+    return {ErrorCode::kInvalidParameter,
+            "invalid transform block width and mv block width: transform block width must be <= mv "
+            "block width"};
+  if (cfg.transform_block_h > cfg.mv_block_h)
+    return {ErrorCode::kInvalidParameter,
+            "invalid transform block height and mv block height: transform block height must be <= "
+            "mv block height"};
+  if (cfg.mv_block_w % cfg.transform_block_w != 0)
+    return {ErrorCode::kInvalidParameter,
+            "invalid mv block width and transform block width: mv block width must be divisible by "
+            "transform block width"};
+  if (cfg.mv_block_h % cfg.transform_block_h != 0)
+    return {ErrorCode::kInvalidParameter,
+            "invalid mv block height and transform block height: mv block height must be divisible "
+            "by transform block height"};
+  return {ErrorCode::kOk, ""};
+}
+
+static void check(int rc) {
+  if (rc != SVC_OK) throw Error(rc, svc_last_error());
+}
+
+Encoder::Encoder(const EncoderConfig& cfg, const VideoProperties& vidprops,
+                 BoundedQueue<Frame>& in_queue, BoundedQueue<Bytes>& out_queue, BlockTypeFn classify)
+    : cfg_(cfg), vidprops_(vidprops), in_queue_(in_queue), out_queue_(out_queue),
+      classify_(std::move(classify)) {
+  svc_session_config c{};
+  c.struct_size = sizeof(c);
+  c.frame_w = vidprops.frame_w;
+  c.frame_h = vidprops.frame_h;
+  c.mv_block_w = cfg.mv_block_w;
+  c.mv_block_h = cfg.mv_block_h;
+  c.mv_search_range = cfg.mv_search_range;
+  c.pyr_lvl_count = cfg.pyr_lvl_count;
+  c.transform_block_w = cfg.transform_block_w;
+  c.transform_block_h = cfg.transform_block_h;
+  c.device = cfg.device;
+  c.max_batch = cfg.max_batch;
+  check(svc_session_create(&c, &session_));
+  svc_session_info info{};
+  check(svc_session_info_get(session_, &info));
+  padded_frame_w_ = info.padded_w;  // libs/encoder.cpp:165-175
+  padded_frame_h_ = info.padded_h;
+  mv_field_w_ = info.mv_field_w;
+  mv_field_h_ = info.mv_field_h;
+  frame_stream_bytes_ = info.frame_stream_bytes;
+  frame_in_bytes_ = info.frame_in_bytes;
+  const size_t B = info.max_batch, mvn = (size_t)mv_field_w_ * mv_field_h_;
+  h_in_ = static_cast<uchar*>(svc_host_alloc(B * frame_in_bytes_));
+  h_stream_ = static_cast<uchar*>(svc_host_alloc(B * frame_stream_bytes_));
+  h_mv_ = static_cast<float*>(svc_host_alloc(B * mvn * 2 * sizeof(float)));
+  h_mad_ = static_cast<float*>(svc_host_alloc(B * mvn * sizeof(float)));
+  if (!h_in_ || !h_stream_ || !h_mv_ || !h_mad_) throw Error(SVC_ERR_CUDA, "pinned allocation failed");
+}
+
+Encoder::~Encoder() {
+  svc_host_free(h_in_);
+  svc_host_free(h_stream_);
+  svc_host_free(h_mv_);
+  svc_host_free(h_mad_);
+  svc_session_destroy(session_);
+}
+
+void Encoder::operator()() {
+  // Header first (libs/encoder.cpp:361-381): frame_count excludes the tracked-only first frame
+  {
+    Bytes hdr(32);
+    check(svc_write_header(vidprops_.frame_count, vidprops_.frame_w, vidprops_.frame_h, padded_frame_w_,
+                           padded_frame_h_, cfg_.transform_block_w, cfg_.transform_block_h, 3,
+                           hdr.data()));
+    out_queue_.Push(std::move(hdr));
+  }
+  const size_t mvn = (size_t)mv_field_w_ * mv_field_h_;
+  std::vector<uint> block_types(mvn);
+  svc_session_info info{};
+  check(svc_session_info_get(session_, &info));
+  Frame frame;
+  while (true) {
+    // block for one frame, then take whatever else is already queued (<= max_batch)
+    if (!in_queue_.Pop(frame)) break;
+    uint n = 0;
+    do {
+      if (frame.size() != frame_in_bytes_) throw Error(SVC_ERR_INVALID_ARG, "frame has the wrong size");
+      std::memcpy(h_in_ + (size_t)n * frame_in_bytes_, frame.data(), frame_in_bytes_);
+      ++n;
+    } while (n < info.max_batch && in_queue_.TryPop(frame));
+    uint n_enc = 0;
+    check(svc_session_encode(session_, h_in_, n, h_mv_, h_mad_, h_stream_, nullptr, &n_enc));
+    for (uint i = 0; i < n_enc; ++i) {
+      uchar* rec = h_stream_ + (size_t)i * frame_stream_bytes_;
+      if (classify_) {
+        std::fill(block_types.begin(), block_types.end(), 0u);  // BLOCK_TYPE_BACKGROUND, libs/encoder.cpp:549-551
+        classify_(reinterpret_cast<const Vec2f*>(h_mv_ + (size_t)i * mvn * 2), h_mad_ + (size_t)i * mvn,
+                  mv_field_w_, mv_field_h_, block_types.data());
+        check(svc_patch_block_types(rec, vidprops_.frame_w, vidprops_.frame_h, cfg_.transform_block_w,
+                                    cfg_.transform_block_h, 3, cfg_.mv_block_w, cfg_.mv_block_h,
+                                    mv_field_w_, block_types.data()));
+      }
+      out_queue_.Push(Bytes(rec, rec + frame_stream_bytes_));
+      ++frames_encoded_;
+    }
+  }
+  out_queue_.SignalProducerIsDone();  // libs/encoder.cpp:666
+}
+
+}  // namespace svc

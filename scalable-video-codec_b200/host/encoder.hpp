@@ -1,0 +1,150 @@
+// encoder.hpp -- C++ host driver of the device-resident hot path: the
+// counterpart of the reference's Encoder functor (libs/encoder.hpp:52-95,
+// libs/encoder.cpp:341-671) with its OpenCV buffers replaced by one
+// svc_session on one GPU.
+//
+// Same contract towards the application (apps/encoder.cpp:172-228): frames
+// are popped from an input queue until the producer is done, the first byte
+// buffer pushed to the output queue is the 32-byte Header
+// (libs/encoder.cpp:361-381), then one serialised frame per encoded frame
+// (libs/encoder.cpp:647-652); the first input frame is tracked-only.  What
+// differs, because the image has no C++ OpenCV: frames are raw interleaved
+// 8-bit BGR buffers instead of cv::Mat3b, and the CPU stages that turn a
+// motion field into block types (RANSAC .. connected components,
+// libs/encoder.cpp:491-624, out of scope for the GPU path) are supplied by the
+// application as a callback; without one every block is BLOCK_TYPE_BACKGROUND.
+// The callback's labels are patched into the records the GPU already wrote
+// (svc_patch_block_types), so the consumers downstream see the reference layout.
+#ifndef SVC_B200_HOST_ENCODER_HPP
+#define SVC_B200_HOST_ENCODER_HPP
+
+#include <condition_variable>
+#include <cstdint>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "motion.hpp"
+
+struct svc_session;
+
+namespace svc {
+
+enum class ErrorCode { kOk, kUnspecified, kInvalidParameter };  // libs/error.hpp:6
+
+struct Status {  // libs/error.hpp:8-11 (Error{code, message})
+  ErrorCode code;
+  std::string message;
+};
+
+// Hot-path subset of EncoderConfig (libs/encoder.hpp:25-37); same field names.
+struct EncoderConfig {
+  uint mv_block_w = 16;         // apps/encoder.cpp:42-58 defaults
+  uint mv_block_h = 16;
+  uint mv_search_range = 8;
+  uint pyr_lvl_count = 4;
+  uint transform_block_w = 8;
+  uint transform_block_h = 8;
+  int device = 0;
+  uint max_batch = 32;  // frames per kernel launch
+};
+
+struct VideoProperties {  // libs/encoder.hpp:46-50
+  uint frame_w;
+  uint frame_h;
+  uint frame_count;
+};
+
+// Validate(const EncoderConfig&), libs/encoder.cpp:62-142 (hot-path fields).
+Status Validate(const EncoderConfig&);
+
+// Bounded blocking queue with the reference's CircularQueue semantics
+// (libs/queue.hpp:13-83): Push blocks when full, Pop returns false once the
+// queue is empty and the producer signalled completion.
+template <typename T>
+class BoundedQueue {
+ public:
+  explicit BoundedQueue(size_t capacity) : cap_(capacity) {}
+  void Push(T v) {
+    std::unique_lock<std::mutex> l(m_);
+    not_full_.wait(l, [&] { return q_.size() < cap_; });
+    q_.push_back(std::move(v));
+    not_empty_.notify_one();
+  }
+  bool Pop(T& out) {
+    std::unique_lock<std::mutex> l(m_);
+    not_empty_.wait(l, [&] { return !q_.empty() || done_; });
+    if (q_.empty()) return false;
+    out = std::move(q_.front());
+    q_.pop_front();
+    not_full_.notify_one();
+    return true;
+  }
+  // Non-blocking variant used to top up a batch without stalling the GPU.
+  bool TryPop(T& out) {
+    std::lock_guard<std::mutex> l(m_);
+    if (q_.empty()) return false;
+    out = std::move(q_.front());
+    q_.pop_front();
+    not_full_.notify_one();
+    return true;
+  }
+  void SignalProducerIsDone() {
+    std::lock_guard<std::mutex> l(m_);
+    done_ = true;
+    not_empty_.notify_all();
+  }
+
+ private:
+  size_t cap_;
+  std::deque<T> q_;
+  bool done_ = false;
+  std::mutex m_;
+  std::condition_variable not_full_, not_empty_;
+};
+
+using Frame = std::vector<uchar>;  // frame_h * frame_w * 3 interleaved BGR
+using Bytes = std::vector<uchar>;
+
+// mv_field / min_mad: mv_field_w * mv_field_h entries of one encoded frame;
+// block_types (out): same count, preset to BLOCK_TYPE_BACKGROUND (0).
+using BlockTypeFn = std::function<void(const Vec2f* mv_field, const float* min_mad, uint mv_field_w,
+                                       uint mv_field_h, uint* block_types)>;
+
+class Encoder {
+ public:
+  Encoder(const EncoderConfig& cfg, const VideoProperties& vidprops, BoundedQueue<Frame>& in_queue,
+          BoundedQueue<Bytes>& out_queue, BlockTypeFn classify = nullptr);
+  ~Encoder();
+  Encoder(const Encoder&) = delete;
+  Encoder& operator=(const Encoder&) = delete;
+  void operator()();
+
+  uint padded_frame_w() const { return padded_frame_w_; }
+  uint padded_frame_h() const { return padded_frame_h_; }
+  uint mv_field_w() const { return mv_field_w_; }
+  uint mv_field_h() const { return mv_field_h_; }
+  uint64_t frames_encoded() const { return frames_encoded_; }
+
+ private:
+  EncoderConfig cfg_;
+  VideoProperties vidprops_;
+  BoundedQueue<Frame>& in_queue_;
+  BoundedQueue<Bytes>& out_queue_;
+  BlockTypeFn classify_;
+  svc_session* session_ = nullptr;
+  uint padded_frame_w_ = 0, padded_frame_h_ = 0, mv_field_w_ = 0, mv_field_h_ = 0;
+  uint64_t frame_stream_bytes_ = 0, frame_in_bytes_ = 0;
+  uint64_t frames_encoded_ = 0;
+  // pinned staging owned by the encoder (svc_host_alloc)
+  uchar* h_in_ = nullptr;
+  uchar* h_stream_ = nullptr;
+  float* h_mv_ = nullptr;
+  float* h_mad_ = nullptr;
+};
+
+}  // namespace svc
+
+#endif  // SVC_B200_HOST_ENCODER_HPP
