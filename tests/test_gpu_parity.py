@@ -252,6 +252,30 @@ def test_session_device_path_full_1080p_properties(gpu, oracle):
             b.free()
 
 
+def test_session_4k_geometry(gpu, oracle):
+    """BASELINE config 4 geometry (3840x2160, no padding): exact motion on one pair, DC property
+    and a sampled coefficient check on the stream."""
+    w, h, n = 3840, 2160, 3
+    seq = SyntheticSequence(w, h, n, seed=44)
+    frames = seq.frames()
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, max_batch=2)) as s:
+        assert (s.padded_w, s.padded_h, s.mv_field_w, s.mv_field_h) == (3840, 2160, 240, 135)
+        assert s.frame_stream_bytes == 480 * 270 * 772
+        mv, mad, st = s.encode(frames)
+        p0, p1 = oracle.y_pyramid(frames[1], w, h, 4), oracle.y_pyramid(frames[2], w, h, 4)
+        emv, emad = oracle.hbma(p0, p1, 8)
+        assert np.array_equal(mv[1], emv) and np.array_equal(mad[1], emad)
+        rec = st[0].view(np.uint32).reshape(270, 480, 193)
+        dc = rec[..., 1::64].view(np.float32)
+        exp = frames[1].reshape(270, 8, 480, 8, 3).astype(np.float64).sum(axis=(1, 3)) / 8.0
+        assert np.abs(dc - exp).max() <= DCT_TOL
+        crop = np.ascontiguousarray(frames[1][1040:1104, 1920:2048])  # 8 x 16 blocks
+        planes = oracle.dct_planar(crop, 128, 64)
+        got = rec[130:138, 240:256, 1:].view(np.float32).reshape(8, 16, 3, 8, 8)
+        exp_blocks = planes.reshape(3, 8, 8, 16, 8).transpose(1, 3, 0, 2, 4)
+        assert np.abs(got - exp_blocks).max() <= DCT_TOL
+
+
 def test_stage_entry_points(gpu, oracle):
     w, h, n = 320, 180, 3
     seq = SyntheticSequence(w, h, n, seed=8)
