@@ -19,6 +19,8 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace svc {
@@ -197,10 +199,14 @@ struct TileGeom {
   }
 };
 
-template <int B, int R>
+// One candidate column: NDY vertically adjacent candidates (dy = 0..NDY-1) of the
+// BxB anchor block `ablk` against the tracked rows starting at `tcol` (row 0 =
+// first candidate row), byte column `sx`.  Streams the B+NDY-1 rows once; rows
+// t >= nrows (only when fewer than NDY candidates are wanted) are not touched.
+template <int B, int NDY, bool kLimitRows>
 __device__ __forceinline__ void sad_column(const uint8_t* __restrict__ tcol, const int PT,
                                            const int sx, const uint8_t* __restrict__ ablk,
-                                           const int PA, uint32_t (&acc)[2 * R + 1]) {
+                                           const int PA, uint32_t (&acc)[NDY], const int nrows) {
   constexpr int NW = B >= 4 ? B / 4 : 1;
   constexpr uint32_t MASK = B >= 4 ? 0xffffffffu : (B == 2 ? 0xffffu : 0xffu);
   uint32_t a[B][NW];
@@ -224,16 +230,16 @@ __device__ __forceinline__ void sad_column(const uint8_t* __restrict__ tcol, con
   const uint8_t* trow = tcol + (sx & ~3);
   const uint32_t sh = (uint32_t)(sx & 3) * 8u;
 #pragma unroll
-  for (int t = 0; t < B + 2 * R; ++t) {
+  for (int t = 0; t < B + NDY - 1; ++t) {
     const uint32_t* q = reinterpret_cast<const uint32_t*>(trow + t * PT);
     uint32_t raw[NW + 1];
 #pragma unroll
-    for (int k = 0; k <= NW; ++k) raw[k] = q[k];
+    for (int k = 0; k <= NW; ++k) raw[k] = (!kLimitRows || t < nrows) ? q[k] : 0u;
     uint32_t tw[NW];
 #pragma unroll
     for (int k = 0; k < NW; ++k) tw[k] = __funnelshift_r(raw[k], raw[k + 1], sh) & MASK;
 #pragma unroll
-    for (int dyi = 0; dyi <= 2 * R; ++dyi) {
+    for (int dyi = 0; dyi < NDY; ++dyi) {
       const int ar = t - dyi;
       if (ar >= 0 && ar < B) {
 #pragma unroll
@@ -270,7 +276,7 @@ __device__ __forceinline__ void tile_level(const uint8_t* smem, const HbmaParams
   uint32_t acc[G];
 #pragma unroll
   for (int i = 0; i < G; ++i) acc[i] = 0;
-  sad_column<B, R>(sT + sy0 * PT, PT, sx, sA + (w * B) * PA + ((tile_bx0 * B) & 15) + g * B, PA, acc);
+  sad_column<B, G, false>(sT + sy0 * PT, PT, sx, sA + (w * B) * PA + ((tile_bx0 * B) & 15) + g * B, PA, acc, 0);
   const bool xok = (x >= 0) && (x <= fw - B);
   const int gbase = g * G;
   constexpr float inv_area = 1.0f / (float)(B * B);
@@ -378,6 +384,160 @@ hbma_tile_kernel(const __grid_constant__ HbmaTileMaps maps, const HbmaParams p) 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Window kernel (16x16 blocks, large top-level range r: the range / level sweep
+// of BASELINE config 3).  One CTA per motion block walks the pyramid.  At each
+// level the clamped search window ((B+2r)^2 bytes, position data dependent on
+// the coarser level's vector) and the anchor block are staged in shared memory
+// by two TMA tensor loads on one mbarrier; work items = (candidate column dx,
+// chunk of 8 candidate rows), spread over the CTA; each item streams B+7 window
+// rows once and feeds 8 running SADs (VABSDIFF4).  Argmin: packed
+// (sad<<16 | scan index) minimum (warp redux + shared memory); the top level
+// additionally keeps every SAD (u16) in shared memory to replay the
+// reference's "every candidate updated => zero vector" rule in parallel.
+// The integer-ALU pipe (VABSDIFF4 + funnel shifts) is the binding resource.
+// ---------------------------------------------------------------------------
+struct HbmaWindowMaps {
+  CUtensorMap t[5];  // tracked window box per level: align16(B+2r+15) x (B+2r)
+  CUtensorMap a[5];  // anchor block box per level: 16 x B
+};
+
+struct WinGeom {
+  uint32_t off_anchor, off_sads, smem_bytes;  // window at offset 0
+  uint32_t box_w[5], box_h[5];
+};
+
+template <int B>
+__device__ __forceinline__ void window_level(const uint8_t* sW, const int PW, const uint8_t* sA,
+                                             uint16_t* sS, uint32_t* sRed, const bool top,
+                                             const int ncx, const int ncy, const int sx_base,
+                                             const int a_off, uint32_t& best_key, bool& any_viol) {
+  constexpr int NDY = 8;
+  const int nch = (ncy + NDY - 1) / NDY;
+  const int n_items = ncx * nch;
+  uint32_t key = 0xffffffffu;
+  for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
+    const int c = item / ncx, dx = item - c * ncx;
+    const int dy0 = c * NDY, ndy = min(NDY, ncy - dy0);
+    uint32_t acc[NDY];
+#pragma unroll
+    for (int i = 0; i < NDY; ++i) acc[i] = 0;
+    sad_column<B, NDY, true>(sW + dy0 * PW, PW, sx_base + dx, sA + a_off, 16, acc, B + ndy - 1);
+#pragma unroll
+    for (int i = 0; i < NDY; ++i) {
+      if (i < ndy) {
+        const uint32_t idx = (uint32_t)((dy0 + i) * ncx + dx);  // scan order inside the clamped window
+        if (top) {
+          sS[idx] = (uint16_t)acc[i];
+          key = min(key, (acc[i] << 16) | (0xffffu - idx));  // "<=": the last minimum wins
+        } else {
+          key = min(key, (acc[i] << 16) | idx);              // "<": the first minimum wins
+        }
+      }
+    }
+  }
+  key = __reduce_min_sync(0xffffffffu, key);
+  if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5] = key;
+  __syncthreads();  // also publishes sS
+  uint32_t best = 0xffffffffu;
+  for (uint32_t i = 0; i < (blockDim.x >> 5); ++i) best = min(best, sRed[i]);
+  best_key = best;
+  bool viol = false;
+  if (top) {
+    const int n = ncx * ncy;
+    for (int i = threadIdx.x + 1; i < n; i += blockDim.x) viol |= sS[i] > sS[i - 1];
+  }
+  any_viol = __syncthreads_or(viol);  // second barrier: sRed / sS / window may be reused after it
+}
+
+__global__ void __launch_bounds__(256)
+hbma_window_kernel(const __grid_constant__ HbmaWindowMaps maps, const __grid_constant__ HbmaParams p,
+                   const __grid_constant__ WinGeom g) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t sRed[8];
+  const uint32_t per_frame = p.mvw * p.mvh;
+  const uint32_t f = blockIdx.x / per_frame, bi = blockIdx.x % per_frame;
+  const int bx = (int)(bi % p.mvw), by = (int)(bi / p.mvw);
+  const int r = (int)p.r, L = (int)p.lay.levels;
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + g.off_anchor;
+  uint16_t* sS = reinterpret_cast<uint16_t*>(smem + g.off_sads);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int mx = 0, my = 0;
+  float cur = FLT_MAX;
+  uint32_t parity = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const bool top = (l == L - 1);
+    const int B = 16 >> l;
+    const int fw = (int)p.lay.w[l], fh = (int)p.lay.h[l];
+    if (!top) { mx *= 2; my *= 2; }
+    const int ax = bx * B, ay = by * B;
+    const int cx = ax + mx, cy = ay + my;
+    const int x0 = max(0, cx - r), x1 = min(fw - B + 1, cx + r + 1);
+    const int y0 = max(0, cy - r), y1 = min(fh - B + 1, cy + r + 1);
+    const int ncx = x1 - x0, ncy = y1 - y0;
+    const int wx = x0 & ~15;  // TMA: 16-byte aligned box origin
+    if (threadIdx.x == 0) {
+      // order the generic-proxy reads of the previous level before the async-proxy overwrite
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                   "r"(g.box_w[l] * g.box_h[l] + 16u * (uint32_t)B) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(sW)), "l"(&maps.t[l]), "r"(wx), "r"(y0), "r"((int)f),
+          "r"(bar_addr) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(sA)), "l"(&maps.a[l]), "r"(ax & ~15), "r"(ay),
+          "r"((int)f + 1), "r"(bar_addr) : "memory");
+    }
+    {
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar_addr), "r"(parity) : "memory");
+      }
+      parity ^= 1u;
+    }
+    uint32_t best;
+    bool any_viol;
+    const int PW = (int)g.box_w[l], sxb = x0 - wx, aoff = ax & 15;
+    switch (B) {
+      case 16: window_level<16>(sW, PW, sA, sS, sRed, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      case 8:  window_level<8>(sW, PW, sA, sS, sRed, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      case 4:  window_level<4>(sW, PW, sA, sS, sRed, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      case 2:  window_level<2>(sW, PW, sA, sS, sRed, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      default: window_level<1>(sW, PW, sA, sS, sRed, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+    }
+    const float m = (float)(best >> 16) * (1.0f / (float)(B * B));
+    const int idx = top ? (int)(0xffffu - (best & 0xffffu)) : (int)(best & 0xffffu);
+    const int nmx = x0 + idx % ncx - ax, nmy = y0 + idx / ncx - ay;
+    if (top) {
+      cur = m;
+      mx = any_viol ? nmx : 0;
+      my = any_viol ? nmy : 0;
+    } else if (m < cur) {
+      cur = m;
+      mx = nmx;
+      my = nmy;
+    }
+  }
+  if (threadIdx.x == 0) {
+    const uint64_t o = (uint64_t)f * per_frame + bi;
+    if (p.mv) p.mv[o] = make_float2((float)mx, (float)my);
+    if (p.mad) p.mad[o] = cur;
+  }
+}
+
 // ---- host side: tensor maps + dispatch -----------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -446,12 +606,51 @@ static bool try_launch_tile(const HbmaParams& p, cudaStream_t st, cudaError_t* e
   return false;
 }
 
+static bool try_launch_window(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
+  const uint32_t L = p.lay.levels, r = p.r;
+  if (p.bw != 16 || p.bh != 16 || L > 5 || r < 1) return false;
+  if (16 + 2 * r + 15 > 256) return false;                 // TMA box limit
+  if ((2 * r + 1) * (2 * r + 1) > 65536) return false;     // 16-bit scan index
+  const uint64_t n_ctas = (uint64_t)p.mvw * p.mvh * p.n_frames;
+  if (n_ctas > 0x7fffffffull) return false;
+  WinGeom g{};
+  HbmaWindowMaps maps;
+  const uint32_t n_slots = p.n_frames + 1;
+  uint32_t win_bytes = 0;
+  for (uint32_t l = 0; l < L; ++l) {
+    const uint32_t B = 16u >> l;
+    g.box_w[l] = (B + 2 * r + 15 + 15) & ~15u;
+    g.box_h[l] = B + 2 * r;
+    win_bytes = std::max(win_bytes, g.box_w[l] * g.box_h[l]);
+    const uint8_t* base = p.pyr + p.lay.off[l];
+    if (!encode_box(&maps.t[l], base, p.lay.w[l], p.lay.h[l], p.lay.pitch[l], p.lay.slot_bytes, n_slots,
+                    g.box_w[l], g.box_h[l]) ||
+        !encode_box(&maps.a[l], base, p.lay.w[l], p.lay.h[l], p.lay.pitch[l], p.lay.slot_bytes, n_slots,
+                    16, B)) {
+      *err = cudaErrorNotSupported;
+      return true;
+    }
+  }
+  g.off_anchor = (win_bytes + 16 + 127) & ~127u;   // +16: one aligned word may be read past a row
+  g.off_sads = g.off_anchor + 256;
+  g.smem_bytes = g.off_sads + (((2 * r + 1) * (2 * r + 1) * 2 + 127) & ~127u);
+  if (g.smem_bytes > 200 * 1024) return false;
+  const uint32_t items = (2 * r + 1) * ((2 * r + 1 + 7) / 8);
+  const uint32_t threads = items <= 64 ? 64 : (items <= 160 ? 128 : 256);
+  *err = cudaFuncSetAttribute(hbma_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)g.smem_bytes);
+  if (*err != cudaSuccess) return true;
+  hbma_window_kernel<<<(uint32_t)n_ctas, threads, g.smem_bytes, st>>>(maps, p, g);
+  *err = cudaGetLastError();
+  return true;
+}
+
 cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches) {
   if (p.n_frames == 0) return cudaSuccess;
   static const bool env_generic = getenv("SVC_HBMA_FORCE_GENERIC") != nullptr;  // test hook
   if (!p.force_generic && !env_generic) {
     cudaError_t e = cudaSuccess;
-    if (try_launch_tile(p, st, &e)) {
+    if (try_launch_tile(p, st, &e) || try_launch_window(p, st, &e)) {
       if (n_launches) *n_launches += 1;
       return e;
     }

@@ -109,6 +109,20 @@ def test_hbma_tiled_path_vs_oracle(gpu, oracle, L, R, w, h):
     assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
 
 
+@pytest.mark.parametrize("L,R", [(4, 64), (4, 100), (3, 32), (3, 60), (2, 32), (2, 10), (1, 3), (1, 8),
+                                 (1, 16), (1, 40), (5, 80), (5, 128)])
+@pytest.mark.parametrize("w,h", [(176, 112), (64, 48)])
+def test_hbma_window_path_vs_oracle(gpu, oracle, L, R, w, h):
+    """16x16 blocks with a large top-level range: the per-block TMA window kernel (windows
+    larger than the frame, clamping on every side, flat-patch ties, zero padding rows)."""
+    pw, ph = gpu.padded_dim(w, 16, L), gpu.padded_dim(h, 16, L)
+    seq = SyntheticSequence(w, h, 2, seed=L * 7 + R)
+    p0, p1 = oracle.y_pyramid(seq.frame(0), pw, ph, L), oracle.y_pyramid(seq.frame(1), pw, ph, L)
+    mv, mad = gpu.EstimateMotionHierarchical(p0, p1, L, pw, ph, R, 16, 16)
+    emv, emad = oracle.hbma(p0, p1, R)
+    assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+
+
 def test_hbma_flat_frames_tie_break(gpu, oracle):
     z = [np.zeros((64 >> l, 96 >> l), np.uint8) for l in range(4)]
     c = [np.full((64 >> l, 96 >> l), 9, np.uint8) for l in range(4)]
