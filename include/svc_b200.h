@@ -211,6 +211,14 @@ int svc_session_synchronize(svc_session* s);
 int svc_session_run_stage(svc_session* s, int stage,
                           const uint8_t* d_frames_bgr, uint32_t n_frames,
                           float* d_mv_xy, float* d_min_mad, uint8_t* d_stream);
+/* Exact SAD work of K2 on pyramid slots 0..n_frames (the pairs run_stage(HBMA) would
+ * process): candidate evaluations and byte-absdiffs, border clamping included, counted
+ * on the device while searching.  Blocking. */
+int svc_session_hbma_work(svc_session* s, uint32_t n_frames, uint64_t* candidates,
+                          uint64_t* absdiffs);
+/* Measured packed-byte SAD issue peak of the device (byte-absdiffs per second of a
+ * dependency-free VABSDIFF4.ACC loop): the integer roofline of the range sweep. */
+int svc_sad_peak(int device, double* absdiffs_per_s);
 /* Number of kernel launches issued by this session so far. */
 uint64_t svc_session_launch_count(const svc_session* s);
 

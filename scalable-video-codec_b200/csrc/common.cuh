@@ -57,8 +57,12 @@ struct HbmaParams {
   float* mad;   // n_frames x mvh x mvw, may be null
   uint32_t n_frames;
   uint32_t force_generic;  // 1 = always take the universal kernel (tests)
+  // optional exact work counters: [0] += candidates, [1] += byte-absdiffs
+  unsigned long long* counters;
 };
 cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches);
+// dependency-free VABSDIFF4.ACC loop: measured packed-byte SAD peak of the device (absdiffs/s)
+cudaError_t measure_sad_peak(cudaStream_t st, double* absdiffs_per_s);
 
 // ---- K3: block DCT + stream layout -------------------------------------------
 struct DctParams {

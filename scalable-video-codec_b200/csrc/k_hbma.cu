@@ -91,6 +91,10 @@ hbma_generic_kernel(HbmaParams p) {
     const int y0 = max(0, cy - r), y1 = min((int)(fh - bh + 1), cy + r + 1);
     const uint32_t ncx = (uint32_t)(x1 - x0);
     const uint32_t n = ncx * (uint32_t)(y1 - y0);
+    if (p.counters && lane == 0) {
+      atomicAdd(p.counters, (unsigned long long)n);
+      atomicAdd(p.counters + 1, (unsigned long long)n * bw * bh);
+    }
 
     uint32_t best_s = 0xffffffffu, best_i = 0;
     bool viol = false;       // some s[i] > s[i-1] (top level only)
@@ -279,6 +283,12 @@ __device__ __forceinline__ void tile_level(const uint8_t* smem, const HbmaParams
   sad_column<B, G, false>(sT + sy0 * PT, PT, sx, sA + (w * B) * PA + ((tile_bx0 * B) & 15) + g * B, PA, acc, 0);
   const bool xok = (x >= 0) && (x <= fw - B);
   const int gbase = g * G;
+  if (p.counters && dxi == 0 && (uint32_t)(tile_bx0 + g) < p.mvw && (uint32_t)(tile_by0 + w) < p.mvh &&
+      (threadIdx.x & 31) / G < Gm::BPW) {
+    const int nx = min(fw - B + 1, cx + R + 1) - max(0, cx - R), ny = min(fh - B + 1, cy + R + 1) - max(0, cy - R);
+    atomicAdd(p.counters, (unsigned long long)(nx * ny));
+    atomicAdd(p.counters + 1, (unsigned long long)(nx * ny) * B * B);
+  }
   constexpr float inv_area = 1.0f / (float)(B * B);
   if constexpr (TOP) {
     const uint32_t xmask = __ballot_sync(0xffffffffu, xok) >> gbase;
@@ -483,6 +493,10 @@ hbma_window_kernel(const __grid_constant__ HbmaWindowMaps maps, const __grid_con
     const int y0 = max(0, cy - r), y1 = min(fh - B + 1, cy + r + 1);
     const int ncx = x1 - x0, ncy = y1 - y0;
     const int wx = x0 & ~15;  // TMA: 16-byte aligned box origin
+    if (p.counters && threadIdx.x == 0) {
+      atomicAdd(p.counters, (unsigned long long)(ncx * ncy));
+      atomicAdd(p.counters + 1, (unsigned long long)(ncx * ncy) * B * B);
+    }
     if (threadIdx.x == 0) {
       // order the generic-proxy reads of the previous level before the async-proxy overwrite
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -663,6 +677,49 @@ cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches) {
   hbma_generic_kernel<<<(uint32_t)blocks, threads, 0, st>>>(p);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
+}
+
+// ---- packed-byte SAD peak ---------------------------------------------------------
+__global__ void __launch_bounds__(256) sad_peak_kernel(uint32_t* out, int iters) {
+  uint32_t a = threadIdx.x * 2654435761u, b = blockIdx.x * 40503u + 1u;
+  uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a), "r"(b));
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += acc[k];
+  if (s == 0x12345u) out[0] = s;  // keep the chain alive
+}
+
+cudaError_t measure_sad_peak(cudaStream_t st, double* absdiffs_per_s) {
+  uint32_t* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, 4);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = kNumSms * 8, threads = 256, iters = 4096;
+  sad_peak_kernel<<<blocks, threads, 0, st>>>(d, 64);  // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0, st);
+    sad_peak_kernel<<<blocks, threads, 0, st>>>(d, iters);
+    cudaEventRecord(e1, st);
+    e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double n = (double)blocks * threads * iters * 8.0 * 4.0;
+    best = std::max(best, n / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  if (absdiffs_per_s) *absdiffs_per_s = best;
+  return e;
 }
 
 }  // namespace svc

@@ -626,6 +626,43 @@ int svc_session_reset(svc_session* s) {
 
 uint64_t svc_session_launch_count(const svc_session* s) { return s ? s->launches : 0; }
 
+int svc_sad_peak(int device, double* absdiffs_per_s) {
+  if (!absdiffs_per_s) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  int rc = prepare_device(device);
+  if (rc) return rc;
+  CU(measure_sad_peak(0, absdiffs_per_s));
+  return SVC_OK;
+}
+
+int svc_session_hbma_work(svc_session* s, uint32_t n_frames, uint64_t* candidates, uint64_t* absdiffs) {
+  if (!s || !candidates || !absdiffs) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  if (n_frames == 0 || n_frames > s->info.max_batch)
+    return fail(SVC_ERR_INVALID_ARG, "n_frames must be in [1, max_batch]");
+  CU(cudaSetDevice(s->device));
+  DevBuf cnt;
+  CU(cnt.alloc(2 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(unsigned long long), s->stream));
+  HbmaParams p{};
+  p.pyr = s->d_pyr;
+  p.lay = s->lay;
+  p.bw = s->cfg.mv_block_w;
+  p.bh = s->cfg.mv_block_h;
+  p.r = s->cfg.mv_search_range >> (s->cfg.pyr_lvl_count - 1);
+  p.mvw = s->info.mv_field_w;
+  p.mvh = s->info.mv_field_h;
+  p.n_frames = n_frames;
+  p.counters = cnt.as<unsigned long long>();
+  int nl = 0;
+  CU(launch_hbma(p, s->stream, &nl));
+  unsigned long long h[2] = {0, 0};
+  CU(cudaMemcpyAsync(h, cnt.p, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  *candidates = h[0];
+  *absdiffs = h[1];
+  s->launches += (uint64_t)nl;
+  return SVC_OK;
+}
+
 int svc_session_synchronize(svc_session* s) {
   if (!s) return fail(SVC_ERR_INVALID_ARG, "null session");
   CU(cudaSetDevice(s->device));

@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.svc_session_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     L.svc_session_encode_device.argtypes = L.svc_session_encode.argtypes
+    L.svc_session_hbma_work.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.svc_session_run_stage.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
     _lib = L
@@ -113,6 +114,13 @@ def device_count() -> int:
     n = C.c_int(0)
     lib().svc_device_count(C.byref(n))
     return n.value
+
+
+def sad_peak(device: int = 0) -> float:
+    """Measured VABSDIFF4 peak of the device in byte-absdiffs per second."""
+    v = C.c_double(0.0)
+    _check(lib().svc_sad_peak(C.c_int(device), C.byref(v)))
+    return v.value
 
 
 def padded_dim(a: int, mv_block: int, levels: int) -> int:
@@ -406,6 +414,12 @@ class Session:
                                                _addr(d_mad), _addr(d_stream),
                                                _addr(d_block_types), C.byref(ne)))
         return ne.value
+
+    def hbma_work(self, n_frames):
+        """(candidates, byte-absdiffs) K2 performs on pyramid slots 0..n_frames, exact."""
+        c, a = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().svc_session_hbma_work(self._h, C.c_uint32(n_frames), C.byref(c), C.byref(a)))
+        return c.value, a.value
 
     def run_stage(self, stage, d_frames, n_frames, d_mv=None, d_mad=None, d_stream=None):
         _check(lib().svc_session_run_stage(self._h, stage, _addr(d_frames), n_frames,

@@ -290,6 +290,29 @@ def test_session_4k_geometry(gpu, oracle):
         assert np.abs(got - exp_blocks).max() <= DCT_TOL
 
 
+@pytest.mark.parametrize("R,L", [(8, 4), (24, 3), (40, 1)])
+def test_device_work_counters_match_oracle(gpu, oracle, R, L):
+    w, h, n = 176, 112, 3
+    frames = SyntheticSequence(w, h, n, seed=R).frames()
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, mv_search_range=R, pyr_lvl_count=L,
+                                       max_batch=4)) as s:
+        d_in = gpu.DeviceBuffer(0, frames.nbytes)
+        d_in.upload(frames)
+        s.run_stage(gpu.STAGE_Y_PYRAMID, d_in, n)
+        cand, absd = s.hbma_work(n)
+        pw, ph = s.padded_w, s.padded_h
+        pyr = [[np.zeros((ph >> l, pw >> l), np.uint8) for l in range(L)]]
+        pyr += [oracle.y_pyramid(f, pw, ph, L) for f in frames]
+        ec = ea = 0
+        for i in range(n):
+            c, a = oracle.hbma_count(pyr[i], pyr[i + 1], R)
+            ec += c
+            ea += a
+        assert (cand, absd) == (ec, ea)
+        d_in.free()
+    assert gpu.sad_peak(0) > 1e12  # > 1 T byte-absdiff/s on any B200
+
+
 def test_stage_entry_points(gpu, oracle):
     w, h, n = 320, 180, 3
     seq = SyntheticSequence(w, h, n, seed=8)
