@@ -25,6 +25,15 @@
 
 namespace svc {
 
+// acc + sum |a.b[i] - b.b[i]| in ONE instruction (VABSDIFF4.U8.ACC with a live accumulator);
+// the __vsadu4() + add form compiles to VABSDIFF4 ..., RZ plus an IADD3 tree, i.e. 1.5x
+// the integer-ALU work.
+__device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t acc) {
+  uint32_t d;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+  return d;
+}
+
 // ---------------------------------------------------------------------------
 // Generic kernel: one warp per MV block, lanes stride over the candidates of
 // the current level, every lane computes whole-block SADs straight from
@@ -49,7 +58,7 @@ __device__ __forceinline__ uint32_t block_sad(const uint8_t* __restrict__ T,
       uint32_t lo = __ldg(t);
       for (uint32_t j = 0; j < bw / 4; ++j) {
         const uint32_t hi = __ldg(t + j + 1);
-        sad = __vsadu4(__funnelshift_r(lo, hi, sh), __ldg(a + j)) + sad;
+        sad = sad4_acc(__funnelshift_r(lo, hi, sh), __ldg(a + j), sad);
         lo = hi;
       }
     }
@@ -247,7 +256,7 @@ __device__ __forceinline__ void sad_column(const uint8_t* __restrict__ tcol, con
       const int ar = t - dyi;
       if (ar >= 0 && ar < B) {
 #pragma unroll
-        for (int k = 0; k < NW; ++k) acc[dyi] = __vsadu4(tw[k], a[ar][k]) + acc[dyi];
+        for (int k = 0; k < NW; ++k) acc[dyi] = sad4_acc(tw[k], a[ar][k], acc[dyi]);
       }
     }
   }
