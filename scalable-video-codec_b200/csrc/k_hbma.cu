@@ -441,7 +441,9 @@ __device__ __forceinline__ void window_level(const uint8_t* sW, const int PW, co
     uint32_t acc[NDY];
 #pragma unroll
     for (int i = 0; i < NDY; ++i) acc[i] = 0;
-    sad_column<B, NDY, true>(sW + dy0 * PW, PW, sx_base + dx, sA + a_off, 16, acc, B + ndy - 1);
+    // the last chunk may hold fewer than NDY rows of candidates: the extra window rows it
+    // streams are slack rows of the staging buffer (never selected below)
+    sad_column<B, NDY, false>(sW + dy0 * PW, PW, sx_base + dx, sA + a_off, 16, acc, 0);
 #pragma unroll
     for (int i = 0; i < NDY; ++i) {
       if (i < ndy) {
@@ -644,7 +646,7 @@ static bool try_launch_window(const HbmaParams& p, cudaStream_t st, cudaError_t*
     const uint32_t B = 16u >> l;
     g.box_w[l] = (B + 2 * r + 15 + 15) & ~15u;
     g.box_h[l] = B + 2 * r;
-    win_bytes = std::max(win_bytes, g.box_w[l] * g.box_h[l]);
+    win_bytes = std::max(win_bytes, g.box_w[l] * (g.box_h[l] + 8));  // + slack rows, see window_level
     const uint8_t* base = p.pyr + p.lay.off[l];
     if (!encode_box(&maps.t[l], base, p.lay.w[l], p.lay.h[l], p.lay.pitch[l], p.lay.slot_bytes, n_slots,
                     g.box_w[l], g.box_h[l]) ||
