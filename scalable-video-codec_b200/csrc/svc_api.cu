@@ -3,6 +3,7 @@
 // three hot-path kernels.  No CPU implementation of any stage exists here: a
 // missing device or a CUDA failure is reported, never worked around.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -389,7 +390,19 @@ struct svc_session {
   cudaStream_t stream = nullptr;  // compute
   bool own_stream = false;
   cudaStream_t s_in = nullptr, s_out = nullptr;  // host path copy streams
-  uint8_t* d_pyr = nullptr;  // max_batch + 1 slots
+  // Two pyramid slot arrays (max_batch + 1 slots each), used by alternate batches so that
+  // K3 of batch k+1 (HBM-bound, main stream) overlaps K1b/K2 of batch k (ALU/latency-bound,
+  // motion stream).  d_pyr aliases array 0 (stage entry points, work counters).
+  uint8_t* d_pyrs[2] = {nullptr, nullptr};
+  uint8_t* d_pyr = nullptr;
+  cudaStream_t s_aux = nullptr;            // motion stream: pyrDown + HBMA
+  cudaEvent_t ev_y = nullptr;              // level-0 luma of the current batch written
+  cudaEvent_t ev_copy = nullptr;           // previous frame's pyramid handed over
+  cudaEvent_t ev_motion[2] = {nullptr, nullptr};  // motion of the batch that used array i done
+  bool motion_pending[2] = {false, false};
+  bool copy_pending = false;
+  uint32_t batch_idx = 0;
+  uint32_t prev_array = 0, prev_slot = 0;  // where the previous frame's pyramid lives
   bool have_prev = false;
   float* d_scratch = nullptr;  // generic DCT path only
   uint32_t scratch_frames = 0;
@@ -401,6 +414,7 @@ struct svc_session {
   uint32_t* d_bt[2] = {nullptr, nullptr};
   cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
   bool staging = false;
+  uint32_t host_chunk = 16;  // frames per pipeline stage of svc_session_encode
   uint64_t launches = 0;
 };
 
@@ -411,13 +425,16 @@ bool needs_scratch(const svc_session* s) {
            s->cfg.frame_w == s->info.padded_w);
 }
 
-// One batch (<= max_batch frames), everything on the device, async on s->stream.
+// One batch (<= max_batch frames), everything on the device.  K3 (+ fused luma) runs on
+// s->stream, the pyramid levels and the motion search on s->s_aux; the caller joins
+// (join_motion) before anything that consumes motion vectors.
 int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, float* d_mv,
                         float* d_mad, uint8_t* d_stream, const uint32_t* d_bt,
                         uint32_t* n_enc_out) {
   const uint32_t first_slot = s->have_prev ? 1u : 0u;
   const uint32_t n_enc = s->have_prev ? m : m - 1;
-  const uint32_t mvn = s->info.mv_field_w * s->info.mv_field_h;
+  const uint32_t cur = s->batch_idx & 1u;
+  uint8_t* pyr = s->d_pyrs[cur];
   int nl = 0;
   DctParams dp{};
   if (n_enc && d_stream) {
@@ -442,29 +459,48 @@ int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, flo
     dp.scratch_frames = s->scratch_frames;
   }
   const bool fuse_y = n_enc && d_stream && dct_can_fuse_y(dp);
+
+  // ---- motion stream, part 1: hand the previous frame's pyramid to slot 0 of this array
+  // (libs/encoder.cpp:661-663 ping-pong).  Ordered after the previous batch's pyramid
+  // build and after the last search that read this array, both on s_aux.
+  // The copy issued by the PREVIOUS batch read the array this batch is about to overwrite.
+  if (s->copy_pending) CU(cudaStreamWaitEvent(s->stream, s->ev_copy, 0));
+  if (s->have_prev) {
+    CU(cudaMemcpyAsync(pyr, s->d_pyrs[s->prev_array] + (size_t)s->prev_slot * s->lay.slot_bytes,
+                       s->lay.slot_bytes, cudaMemcpyDeviceToDevice, s->s_aux));
+    CU(cudaEventRecord(s->ev_copy, s->s_aux));
+    s->copy_pending = true;
+  }
+  // ---- main stream: level-0 luma (fused into K3 when possible)
+  if (s->motion_pending[cur]) CU(cudaStreamWaitEvent(s->stream, s->ev_motion[cur], 0));  // array free
   if (fuse_y) {
     // K3 also emits the level-0 luma of every encoded frame (slots 1..n_enc); a
     // tracked-only first frame (slot 0) still needs the stand-alone conversion.
     if (!s->have_prev) {
-      CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, s->d_pyr, s->lay, 0, 1, s->stream));
+      CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, pyr, s->lay, 0, 1, s->stream));
       nl += 1;
     }
-    dp.y_l0 = s->d_pyr + s->lay.off[0];
+    dp.y_l0 = pyr + s->lay.off[0];
     dp.y_slot_bytes = s->lay.slot_bytes;
     dp.y_first_slot = 1;
     dp.y_pitch = s->lay.pitch[0];
     CU(launch_dct(dp, s->stream, &nl));
   } else {
-    CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, s->d_pyr, s->lay, first_slot, m, s->stream));
+    CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, pyr, s->lay, first_slot, m, s->stream));
     nl += 1;
   }
+  CU(cudaEventRecord(s->ev_y, s->stream));
+  if (n_enc && d_stream && !fuse_y) CU(launch_dct(dp, s->stream, &nl));
+
+  // ---- motion stream, part 2: pyramid levels 1.. and the search
+  CU(cudaStreamWaitEvent(s->s_aux, s->ev_y, 0));
   for (uint32_t l = 0; l + 1 < s->lay.levels; ++l) {
-    CU(launch_pyr_down(s->d_pyr, s->lay, l, first_slot, m, s->stream));
+    CU(launch_pyr_down(pyr, s->lay, l, first_slot, m, s->s_aux));
     nl += 1;
   }
   if (n_enc && (d_mv || d_mad)) {
     HbmaParams p{};
-    p.pyr = s->d_pyr;
+    p.pyr = pyr;
     p.lay = s->lay;
     p.bw = s->cfg.mv_block_w;
     p.bh = s->cfg.mv_block_h;
@@ -474,19 +510,31 @@ int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, flo
     p.mv = reinterpret_cast<float2*>(d_mv);
     p.mad = d_mad;
     p.n_frames = n_enc;
-    CU(launch_hbma(p, s->stream, &nl));
+    CU(launch_hbma(p, s->s_aux, &nl));
   }
-  if (n_enc && d_stream && !fuse_y) CU(launch_dct(dp, s->stream, &nl));
-  // keep the last frame's pyramid as the next tracked frame (libs/encoder.cpp:661-663)
-  const uint32_t last = first_slot + m - 1;
-  if (last != 0) {
-    CU(cudaMemcpyAsync(s->d_pyr, s->d_pyr + (size_t)last * s->lay.slot_bytes, s->lay.slot_bytes,
-                       cudaMemcpyDeviceToDevice, s->stream));
-  }
+  CU(cudaEventRecord(s->ev_motion[cur], s->s_aux));
+  s->motion_pending[cur] = true;
+  s->prev_array = cur;
+  s->prev_slot = first_slot + m - 1;
   s->have_prev = true;
+  s->batch_idx += 1;
   s->launches += (uint64_t)nl;
-  (void)mvn;
   if (n_enc_out) *n_enc_out = n_enc;
+  return SVC_OK;
+}
+
+// Make `st` wait for every motion search issued so far.
+int join_motion(svc_session* s, cudaStream_t st) {
+  for (int i = 0; i < 2; ++i)
+    if (s->motion_pending[i]) CU(cudaStreamWaitEvent(st, s->ev_motion[i], 0));
+  return SVC_OK;
+}
+
+// Order the motion stream after everything already queued on the main stream (results of
+// an earlier call may still be read there).
+int fork_motion(svc_session* s) {
+  CU(cudaEventRecord(s->ev_y, s->stream));
+  CU(cudaStreamWaitEvent(s->s_aux, s->ev_y, 0));
   return SVC_OK;
 }
 
@@ -576,15 +624,30 @@ int svc_session_create(const svc_session_config* cfg, svc_session** out) {
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate"));
     s->own_stream = true;
   }
-  e = cudaMalloc(&s->d_pyr, (size_t)(s->info.max_batch + 1) * s->lay.slot_bytes + kSlack);
-  if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(pyramids)"));
-  e = cudaMemsetAsync(s->d_pyr, 0, (size_t)(s->info.max_batch + 1) * s->lay.slot_bytes + kSlack, s->stream);
-  if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemset(pyramids)"));
+  const size_t pyr_bytes = (size_t)(s->info.max_batch + 1) * s->lay.slot_bytes + kSlack;
+  for (int i = 0; i < 2; ++i) {
+    e = cudaMalloc(&s->d_pyrs[i], pyr_bytes);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(pyramids)"));
+    e = cudaMemsetAsync(s->d_pyrs[i], 0, pyr_bytes, s->stream);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemset(pyramids)"));
+    e = cudaEventCreateWithFlags(&s->ev_motion[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
+  }
+  s->d_pyr = s->d_pyrs[0];
+  e = cudaStreamCreateWithFlags(&s->s_aux, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate(motion)"));
+  e = cudaEventCreateWithFlags(&s->ev_y, cudaEventDisableTiming);
+  if (e != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
+  e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming);
+  if (e != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
+  e = cudaStreamSynchronize(s->stream);  // the memsets, before the motion stream may touch the arrays
+  if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamSynchronize"));
   if (needs_scratch(s)) {
     s->scratch_frames = std::min<uint32_t>(s->info.max_batch, 4);
     e = cudaMalloc(&s->d_scratch, (size_t)s->scratch_frames * 6 * pw * ph * sizeof(float));
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(scratch)"));
   }
+  if (const char* hc = getenv("SVC_HOST_CHUNK")) s->host_chunk = std::max(1, atoi(hc));  // tuning hook
   *out = s;
   return SVC_OK;
 }
@@ -603,7 +666,14 @@ void svc_session_destroy(svc_session* s) {
     if (s->ev_comp[b]) cudaEventDestroy(s->ev_comp[b]);
     if (s->ev_out[b]) cudaEventDestroy(s->ev_out[b]);
   }
-  cudaFree(s->d_pyr);
+  if (s->s_aux) cudaStreamSynchronize(s->s_aux);
+  cudaFree(s->d_pyrs[0]);
+  cudaFree(s->d_pyrs[1]);
+  if (s->ev_y) cudaEventDestroy(s->ev_y);
+  if (s->ev_copy) cudaEventDestroy(s->ev_copy);
+  for (int i = 0; i < 2; ++i)
+    if (s->ev_motion[i]) cudaEventDestroy(s->ev_motion[i]);
+  if (s->s_aux) cudaStreamDestroy(s->s_aux);
   cudaFree(s->d_scratch);
   if (s->s_in) cudaStreamDestroy(s->s_in);
   if (s->s_out) cudaStreamDestroy(s->s_out);
@@ -667,6 +737,7 @@ int svc_session_synchronize(svc_session* s) {
   if (!s) return fail(SVC_ERR_INVALID_ARG, "null session");
   CU(cudaSetDevice(s->device));
   CU(cudaStreamSynchronize(s->stream));
+  CU(cudaStreamSynchronize(s->s_aux));
   return SVC_OK;
 }
 
@@ -680,6 +751,8 @@ int svc_session_encode_device(svc_session* s, const uint8_t* d_frames, uint32_t 
   CU(cudaSetDevice(s->device));
   const size_t mvn = (size_t)s->info.mv_field_w * s->info.mv_field_h;
   uint32_t done_in = 0, done_enc = 0;
+  int rcf = fork_motion(s);
+  if (rcf) return rcf;
   while (done_in < n_frames) {
     const uint32_t m = std::min(s->info.max_batch, n_frames - done_in);
     uint32_t ne = 0;
@@ -692,6 +765,9 @@ int svc_session_encode_device(svc_session* s, const uint8_t* d_frames, uint32_t 
     done_in += m;
     done_enc += ne;
   }
+  // everything the call produced is complete once the session stream gets here
+  int rcj = join_motion(s, s->stream);
+  if (rcj) return rcj;
   if (n_encoded) *n_encoded = done_enc;
   return SVC_OK;
 }
@@ -712,7 +788,9 @@ int svc_session_encode(svc_session* s, const uint8_t* frames, uint32_t n_frames,
   // 3-stage pipeline over batches: H2D (s_in) | kernels (stream) | D2H (s_out)
   while (done_in < n_frames) {
     const int b = chunk & 1;
-    const uint32_t m = std::min(s->info.max_batch, n_frames - done_in);
+    // PCIe-bound: small chunks keep H2D | kernels | D2H overlapped and the exposed head
+    // and tail of the pipeline short
+    const uint32_t m = std::min(std::min(s->info.max_batch, s->host_chunk), n_frames - done_in);
     const uint32_t ne = s->have_prev ? m : m - 1;
     if (chunk >= 2) {
       CU(cudaStreamWaitEvent(s->s_in, s->ev_comp[b], 0));   // d_in[b] consumed
@@ -732,6 +810,8 @@ int svc_session_encode(svc_session* s, const uint8_t* frames, uint32_t n_frames,
     if (rc) return rc;
     CU(cudaEventRecord(s->ev_comp[b], s->stream));
     CU(cudaStreamWaitEvent(s->s_out, s->ev_comp[b], 0));
+    rc = join_motion(s, s->s_out);  // motion vectors come from the motion stream
+    if (rc) return rc;
     if (ne2) {
       if (mv)
         CU(cudaMemcpyAsync(mv + done_enc * mvn * 2, s->d_mv[b], ne2 * mvn * sizeof(float2),
@@ -750,6 +830,7 @@ int svc_session_encode(svc_session* s, const uint8_t* frames, uint32_t n_frames,
   }
   CU(cudaStreamSynchronize(s->s_in));
   CU(cudaStreamSynchronize(s->stream));
+  CU(cudaStreamSynchronize(s->s_aux));
   CU(cudaStreamSynchronize(s->s_out));
   if (n_encoded) *n_encoded = done_enc;
   return SVC_OK;
