@@ -150,18 +150,22 @@ pyr_down_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t first_s
     const bool lane_on = tx < kPdChunks && cx <= need_hi && cx + 15 >= need_lo;
     const bool lane_fast = cx >= 0 && cx + 16 <= (int)sw;
     const int k_lo = max(need_lo - cx, 0), k_hi = min(need_hi - cx, 15);  // border chunk: bytes to fill
+    // interior chunks go global -> shared with cp.async (no register staging, every row's
+    // copy in flight at once); border chunks are patched byte by byte
     for (int row = ty; row < n_rows; row += 4) {
       const uint8_t* srow = src + (uint64_t)reflect101_near(sy0 + row, (int)sh) * spitch;
       uint8_t* trow = tile + row * kPdSrcW + tx * 16;
       if (lane_on) {
         if (lane_fast) {
-          *reinterpret_cast<uint4*>(trow) = __ldg(reinterpret_cast<const uint4*>(srow + cx));
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(trow);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srow + cx) : "memory");
         } else {
 #pragma unroll 1
           for (int k = k_lo; k <= k_hi; ++k) trow[k] = srow[reflect101_near(cx + k, (int)sw)];
         }
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncthreads();
 
