@@ -1,0 +1,111 @@
+// apps/encoder.cpp -- the encoder application on the GPU hot path: counterpart of the
+// reference's apps/encoder.cpp (three threads: reader -> Encoder -> writer, bounded
+// queues of capacity 10, :172-173, :223-228; byte stream on stdout, :154-169).
+//
+// The reference decodes a video file with cv::VideoCapture (:192-204); this image has
+// no C++ OpenCV, so the frame source is raw interleaved 8-bit BGR (file or stdin), e.g.
+//   ffmpeg -i in.mp4 -f rawvideo -pix_fmt bgr24 - | svc_encoder --width W --height H - > out.svc
+// Options keep the reference's names (apps/encoder.cpp:75-104) for the hot-path fields.
+// Block types: every block BLOCK_TYPE_BACKGROUND unless the CPU segmentation stages
+// (RANSAC .. connected components, out of scope here) are supplied through
+// svc::Encoder's callback by an embedding application.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+
+#include "../host/encoder.hpp"
+
+static void usage() {
+  std::fprintf(stderr,
+               "usage: svc_encoder --width W --height H [--frames N] [--mv-search-range R]\n"
+               "                   [--pyr-lvl-count L] [--mv-block-w B] [--mv-block-h B]\n"
+               "                   [--transform-block-w T] [--transform-block-h T] [--device D]\n"
+               "                   [--batch K] [--verbose 0|1] <raw-bgr-file | ->\n");
+}
+
+int main(int argc, char** argv) {
+  svc::EncoderConfig cfg;  // defaults of apps/encoder.cpp:42-58
+  unsigned width = 0, height = 0, frames = 0;
+  int verbose = 1;
+  const char* path = nullptr;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto val = [&](unsigned& out) {
+      if (i + 1 >= argc) { usage(); std::exit(EXIT_FAILURE); }
+      out = (unsigned)std::strtoul(argv[++i], nullptr, 10);
+    };
+    unsigned tmp;
+    if (a == "--width") val(width);
+    else if (a == "--height") val(height);
+    else if (a == "--frames") val(frames);
+    else if (a == "--mv-search-range") val(cfg.mv_search_range);
+    else if (a == "--pyr-lvl-count") val(cfg.pyr_lvl_count);
+    else if (a == "--mv-block-w") val(cfg.mv_block_w);
+    else if (a == "--mv-block-h") val(cfg.mv_block_h);
+    else if (a == "--transform-block-w") val(cfg.transform_block_w);
+    else if (a == "--transform-block-h") val(cfg.transform_block_h);
+    else if (a == "--batch") val(cfg.max_batch);
+    else if (a == "--device") { val(tmp); cfg.device = (int)tmp; }
+    else if (a == "--verbose") { val(tmp); verbose = (int)tmp; }
+    else if (a == "-" || a[0] != '-') path = argv[i];
+    else { usage(); return EXIT_FAILURE; }
+  }
+  if (!path || !width || !height) { usage(); return EXIT_FAILURE; }
+  const svc::Status st = svc::Validate(cfg);
+  if (st.code != svc::ErrorCode::kOk) {  // apps/encoder.cpp:185-190
+    std::fprintf(stderr, "Invalid encoder configuration: %s\n", st.message.c_str());
+    return EXIT_FAILURE;
+  }
+  FILE* in = std::strcmp(path, "-") == 0 ? stdin : std::fopen(path, "rb");
+  if (!in) { std::fprintf(stderr, "Failed to open %s\n", path); return EXIT_FAILURE; }
+  const size_t fbytes = (size_t)width * height * 3;
+  if (!frames && in != stdin) {  // frame count from the file size (the header needs it up front)
+    std::fseek(in, 0, SEEK_END);
+    frames = (unsigned)(std::ftell(in) / (long)fbytes);
+    std::fseek(in, 0, SEEK_SET);
+  }
+  if (!frames) { std::fprintf(stderr, "--frames is required when reading stdin\n"); return EXIT_FAILURE; }
+  if (verbose) std::fprintf(stderr, "frame width: %u\nframe height: %u\nframe count: %u\n", width, height, frames);
+
+  svc::BoundedQueue<svc::Frame> in_queue(10);
+  svc::BoundedQueue<svc::Bytes> out_queue(10);
+  int rc = EXIT_SUCCESS;
+  try {
+    svc::Encoder encoder(cfg, svc::VideoProperties{width, height, frames}, in_queue, out_queue);
+    std::thread reader([&] {
+      svc::Frame f(fbytes);
+      for (unsigned i = 0; i < frames; ++i) {
+        if (std::fread(f.data(), 1, fbytes, in) != fbytes) break;
+        in_queue.Push(f);
+      }
+      in_queue.SignalProducerIsDone();
+    });
+    std::thread writer([&] {
+      svc::Bytes b;
+      while (out_queue.Pop(b)) {
+        if (std::fwrite(b.data(), 1, b.size(), stdout) != b.size()) {
+          std::fprintf(stderr, "Failed to write bytes.\n");  // apps/encoder.cpp:163-167
+          rc = EXIT_FAILURE;
+        }
+      }
+      std::fflush(stdout);
+    });
+    try {
+      encoder();
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "svc_encoder: %s\n", e.what());
+      rc = EXIT_FAILURE;
+      in_queue.SignalProducerIsDone();
+      out_queue.SignalProducerIsDone();
+    }
+    reader.join();
+    writer.join();
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "svc_encoder: %s\n", e.what());
+    rc = EXIT_FAILURE;
+  }
+  if (in != stdin) std::fclose(in);
+  return rc;
+}

@@ -147,22 +147,27 @@ pyr_down_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t first_s
     const int n_rows = 2 * (ye - y0t) + 3;
     const int cx = sx0 + tx * 16;
     const int need_lo = 2 * x0t - 2, need_hi = 2 * xe;  // source columns the outputs read
-    const bool lane_on = tx < kPdChunks && cx <= need_hi && cx + 15 >= need_lo;
-    const bool lane_fast = cx >= 0 && cx + 16 <= (int)sw;
-    const int k_lo = max(need_lo - cx, 0), k_hi = min(need_hi - cx, 15);  // border chunk: bytes to fill
-    // interior chunks go global -> shared with cp.async (no register staging, every row's
-    // copy in flight at once); border chunks are patched byte by byte
+    // chunks completely inside the image: global -> shared with cp.async (no register
+    // staging, every row's copy in flight at once, no divergence)
+    const bool lane_fast = tx < kPdChunks && cx <= need_hi && cx + 15 >= need_lo && cx >= 0 &&
+                           cx + 16 <= (int)sw;
     for (int row = ty; row < n_rows; row += 4) {
       const uint8_t* srow = src + (uint64_t)reflect101_near(sy0 + row, (int)sh) * spitch;
-      uint8_t* trow = tile + row * kPdSrcW + tx * 16;
-      if (lane_on) {
-        if (lane_fast) {
-          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(trow);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srow + cx) : "memory");
-        } else {
-#pragma unroll 1
-          for (int k = k_lo; k <= k_hi; ++k) trow[k] = srow[reflect101_near(cx + k, (int)sw)];
-        }
+      if (lane_fast) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + row * kPdSrcW + tx * 16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srow + cx) : "memory");
+      }
+    }
+    // border columns (left of 0, or from the last whole 16-byte chunk on): thread = row,
+    // a handful of bytes each, through the reflection
+    const int left_hi = min(-1, need_hi);               // columns need_lo .. left_hi
+    const int right_lo = max((int)sw & ~15, need_lo);   // columns right_lo .. need_hi
+    if (need_lo < 0 || need_hi >= ((int)sw & ~15)) {
+      for (int row = threadIdx.x; row < n_rows; row += 128) {
+        const uint8_t* srow = src + (uint64_t)reflect101_near(sy0 + row, (int)sh) * spitch;
+        uint8_t* trow = tile + row * kPdSrcW - sx0;
+        for (int k = need_lo; k <= left_hi; ++k) trow[k] = srow[reflect101_near(k, (int)sw)];
+        for (int k = right_lo; k <= need_hi; ++k) trow[k] = srow[reflect101_near(k, (int)sw)];
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -181,14 +186,15 @@ pyr_down_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t first_s
   for (int y = 0; y < kRpt; ++y) acc[y][0] = acc[y][1] = 0;
 #pragma unroll
   for (int r = 0; r < kRows; ++r) {
-    const uint2 a = *reinterpret_cast<const uint2*>(tcol + r * kPdSrcW);        // tile cols 8tx+8 ..
-    const uint2 b = *reinterpret_cast<const uint2*>(tcol + r * kPdSrcW + 8);    // tile cols 8tx+16 ..
-    const uint32_t c = *reinterpret_cast<const uint32_t*>(tcol + r * kPdSrcW + 16);
-    // p[j] = tile col 8tx+14+j.  h[i] = dp4a(p[2i..2i+3], {1,4,6,4}) + p[2i+4]
-    const uint32_t h0 = __dp4a(__funnelshift_r(a.y, b.x, 16), 0x04060401u, (b.x >> 16) & 0xffu);
-    const uint32_t h1 = __dp4a(b.x, 0x04060401u, b.y & 0xffu);
-    const uint32_t h2 = __dp4a(__funnelshift_r(b.x, b.y, 16), 0x04060401u, (b.y >> 16) & 0xffu);
-    const uint32_t h3 = __dp4a(b.y, 0x04060401u, c & 0xffu);
+    const uint32_t a1 = *reinterpret_cast<const uint32_t*>(tcol + r * kPdSrcW + 4);  // tile cols 8tx+12..15
+    const uint2 b = *reinterpret_cast<const uint2*>(tcol + r * kPdSrcW + 8);           // tile cols 8tx+16..23
+    const uint32_t c = *reinterpret_cast<const uint32_t*>(tcol + r * kPdSrcW + 16);     // tile cols 8tx+24..27
+    // p[j] = tile col 8tx+14+j; h[i] = p[2i] + 4 p[2i+1] + 6 p[2i+2] + 4 p[2i+3] + p[2i+4] as two
+    // packed-byte dot products over the two aligned words the five taps straddle
+    const uint32_t h0 = __dp4a(b.x, 0x00010406u, __dp4a(a1, 0x04010000u, 0u));   // cols 14..18
+    const uint32_t h1 = __dp4a(b.y, 0x00000001u, __dp4a(b.x, 0x04060401u, 0u));  // cols 16..20
+    const uint32_t h2 = __dp4a(b.y, 0x00010406u, __dp4a(b.x, 0x04010000u, 0u));  // cols 18..22
+    const uint32_t h3 = __dp4a(c, 0x00000001u, __dp4a(b.y, 0x04060401u, 0u));    // cols 20..24
     const uint32_t hp0 = h1 * 65536u + h0, hp1 = h3 * 65536u + h2;
 #pragma unroll
     for (int y = 0; y < kRpt; ++y) {

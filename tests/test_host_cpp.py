@@ -29,3 +29,47 @@ def test_host_layer_encoder_matches_oracle(gpu):
     _build()
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PASS frames=6" in r.stdout, r.stdout + r.stderr
+
+
+ENC = os.path.join(PKG, "bin", "svc_encoder")
+
+
+def _build_app():
+    subprocess.run(["make", "-C", PKG, "bin/svc_encoder"], check=True, stdout=subprocess.DEVNULL)
+
+
+def test_encoder_app_rejects_bad_config_like_the_reference(tmp_path):
+    _build_app()
+    raw = tmp_path / "in.bgr"
+    raw.write_bytes(bytes(64 * 48 * 3 * 2))
+    r = subprocess.run([ENC, "--width", "64", "--height", "48", "--mv-search-range", "4", str(raw)],
+                       capture_output=True, timeout=60)
+    assert r.returncode != 0
+    assert b"Invalid encoder configuration" in r.stderr and b"quotient" in r.stderr
+    assert subprocess.run([ENC], capture_output=True, timeout=60).returncode != 0  # usage
+
+
+@pytest.mark.gpu
+def test_encoder_app_stream_matches_oracle(gpu, oracle, tmp_path):
+    import numpy as np
+    from svc_b200.synth import SyntheticSequence
+    _build_app()
+    w, h, n = 320, 180, 6
+    frames = SyntheticSequence(w, h, n, seed=31).frames()
+    raw = tmp_path / "in.bgr"
+    raw.write_bytes(frames.tobytes())
+    r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "4", "--verbose", "0", str(raw)],
+                       capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = np.frombuffer(r.stdout, np.uint8)
+    pw, ph = oracle.padded_dim(w, 16, 4), oracle.padded_dim(h, 16, 4)
+    fb = oracle.serialized_frame_bytes(w, h)
+    assert out.size == 32 + (n - 1) * fb
+    assert np.array_equal(out[:32], oracle.header(n, w, h, pw, ph))
+    for i in range(1, n):
+        exp = oracle.serialize_frame(oracle.dct_planar(frames[i], pw, ph), None, w, h, 8, 8, pw // 16, 16, 16)
+        got = out[32 + (i - 1) * fb: 32 + i * fb]
+        g = got.view(np.uint32).reshape(-1, 193)
+        e = exp.view(np.uint32).reshape(-1, 193)
+        assert not g[:, 0].any()
+        assert np.abs(g[:, 1:].view(np.float32) - e[:, 1:].view(np.float32)).max() <= 1e-3
