@@ -634,7 +634,13 @@ int svc_session_create(const svc_session_config* cfg, svc_session** out) {
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
   }
   s->d_pyr = s->d_pyrs[0];
-  e = cudaStreamCreateWithFlags(&s->s_aux, cudaStreamNonBlocking);
+  {
+    // highest priority: as K3's CTAs retire, the pending pyrDown / HBMA CTAs of the previous
+    // batch are placed first, so the ALU-bound motion work co-runs with the HBM-bound K3
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    e = cudaStreamCreateWithPriority(&s->s_aux, cudaStreamNonBlocking, prio_hi);
+  }
   if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate(motion)"));
   e = cudaEventCreateWithFlags(&s->ev_y, cudaEventDisableTiming);
   if (e != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
