@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--frames", type=int, default=300, help="input frames per GPU per step")
-    ap.add_argument("--batch", type=int, default=64, help="frames per kernel launch")
+    ap.add_argument("--batch", type=int, default=100, help="max frames per kernel launch")
     ap.add_argument("--search-range", type=int, default=8)
     ap.add_argument("--levels", type=int, default=4)
     ap.add_argument("--cpu-sample-frames", type=int, default=33,
