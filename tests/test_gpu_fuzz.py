@@ -1,0 +1,57 @@
+"""GPU: seeded random configurations through the session API against the oracle --
+frame sizes that pad on either/both axes, tiny frames, every level count, non-default MV
+and transform blocks (generic kernels), search ranges on all three HBMA kernels,
+uneven pushes, block types."""
+import numpy as np
+import pytest
+
+from svc_b200.synth import SyntheticSequence
+
+pytestmark = pytest.mark.gpu
+DCT_TOL = 1e-3
+
+
+def _configs(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        L = int(rng.integers(1, 6))
+        mb = int(rng.choice([8, 16, 16, 16, 32]))
+        if mb % (1 << (L - 1)):
+            continue
+        tb = int(rng.choice([t for t in (2, 4, 8, 8, 8, 16) if t <= mb and mb % t == 0]))
+        r_top = int(rng.choice([1, 1, 2, 3, 4, 6, 9]))
+        R = r_top * (1 << (L - 1)) + int(rng.integers(0, 1 << (L - 1)))
+        w = int(rng.integers(8, 200))
+        h = int(rng.integers(8, 140))
+        n_frames = int(rng.integers(2, 5))
+        batch = int(rng.integers(1, 4))
+        out.append((w, h, L, mb, tb, R, n_frames, batch))
+    return out
+
+
+@pytest.mark.parametrize("cfg", _configs(36, 2026))
+def test_random_session_config(gpu, oracle, cfg):
+    w, h, L, mb, tb, R, n, batch = cfg
+    frames = SyntheticSequence(w, h, n, seed=w * 131 + h, n_rects=2).frames()
+    sc = gpu.SessionConfig(frame_w=w, frame_h=h, mv_block_w=mb, mv_block_h=mb, mv_search_range=R,
+                           pyr_lvl_count=L, transform_block_w=tb, transform_block_h=tb, max_batch=batch)
+    with gpu.Session(sc) as s:
+        pw, ph = s.padded_w, s.padded_h
+        assert (pw, ph) == (oracle.padded_dim(w, mb, L), oracle.padded_dim(h, mb, L))
+        rng = np.random.default_rng(7)
+        bt = rng.integers(0, 4, size=(n - 1, s.mv_field_h * s.mv_field_w)).astype(np.uint32)
+        mv, mad, st = s.encode(frames, block_types=bt)
+        assert mv.shape[0] == n - 1
+        rec = 1 + 3 * tb * tb
+        pyr = [oracle.y_pyramid(f, pw, ph, L) for f in frames]
+        for i in range(1, n):
+            emv, emad = oracle.hbma(pyr[i - 1], pyr[i], R, mb, mb)
+            assert np.array_equal(mv[i - 1], emv), (cfg, i)
+            assert np.array_equal(mad[i - 1], emad), (cfg, i)
+            planes = oracle.dct_planar(frames[i], pw, ph, tb, tb)
+            exp = oracle.serialize_frame(planes, bt[i - 1], w, h, tb, tb, pw // mb, mb, mb)
+            g = st[i - 1].view(np.uint32).reshape(-1, rec)
+            e = exp.view(np.uint32).reshape(-1, rec)
+            assert np.array_equal(g[:, 0], e[:, 0]), (cfg, i)
+            assert np.abs(g[:, 1:].view(np.float32) - e[:, 1:].view(np.float32)).max() <= DCT_TOL, (cfg, i)
