@@ -222,6 +222,33 @@ int svc_sad_peak(int device, double* absdiffs_per_s);
 /* Number of kernel launches issued by this session so far. */
 uint64_t svc_session_launch_count(const svc_session* s);
 
+/* ------------------------------------------------------------------------
+ * Decoder block path (the inverse of K3)
+ * ---------------------------------------------------------------------- */
+typedef struct svc_rect { uint32_t x, y, w, h; } svc_rect;
+
+/* CalcWithinFrameRectFromCenter + the scaling of the gaze rectangle to the padded
+ * frame -- libs/decoder.cpp:66-98, 172-189 (pure host arithmetic). */
+int svc_gaze_rect(uint32_t gaze_x, uint32_t gaze_y, uint32_t max_gaze_rect_w,
+                  uint32_t max_gaze_rect_h, uint32_t frame_w, uint32_t frame_h,
+                  uint32_t padded_w, uint32_t padded_h, svc_rect* out);
+
+/* ParseBlock + DecodeBlock for every record of one frame -- libs/decoder.cpp:102-149 over
+ * the loop at :191-213.  frame_records: (padded_w/tbw)*(padded_h/tbh) records in raster
+ * order; quantisation step 1 for blocks whose top-left corner is inside `gaze` (may be
+ * NULL), background step for block type 0, foreground step otherwise (DecoderConfig,
+ * libs/decoder.hpp:12-17; defaults 1 / 640, apps/decoder.cpp:20-25).  out_bgr: padded_h x
+ * padded_w x 3 interleaved float -- the `upscaled_frame` before the division by 255 and
+ * the resize.  8x8 transform blocks only. */
+int svc_decode_frame_blocks(const uint8_t* frame_records, uint32_t padded_w, uint32_t padded_h,
+                            uint32_t tbw, uint32_t tbh, uint32_t fg_quant_step,
+                            uint32_t bg_quant_step, const svc_rect* gaze, float* out_bgr);
+/* Same for n_frames frames resident on `device`; asynchronous on `cuda_stream`. */
+int svc_decode_frames_device(int device, void* cuda_stream, const uint8_t* d_records,
+                             uint32_t n_frames, uint32_t padded_w, uint32_t padded_h,
+                             uint32_t tbw, uint32_t tbh, uint32_t fg_quant_step,
+                             uint32_t bg_quant_step, const svc_rect* gaze, float* d_out_bgr);
+
 /* Memory helpers so that non-CUDA hosts (ctypes, cgo, JNI) need no runtime. */
 void* svc_host_alloc(size_t bytes); /* pinned */
 void svc_host_free(void* p);

@@ -189,3 +189,21 @@ def serialize_frame(planes, block_types, w, h, tbw, tbh, mv_field_w,
                               tbw, tbh, mv_field_w, mv_block_w, mv_block_h,
                               _ptr(out))
     return out
+
+
+def gaze_rect(gx, gy, max_w, max_h, fw, fh, pw, ph):
+    out = (C.c_uint * 4)()
+    lib().orc_gaze_rect(gx, gy, max_w, max_h, fw, fh, pw, ph, out)
+    return tuple(int(v) for v in out)
+
+
+def decode_frame_blocks(records, pw, ph, tbw=8, tbh=8, fg_q=1, bg_q=640, gaze=None):
+    """(ph, pw, 3) float32: the decoder's `upscaled_frame` before /255 and resize."""
+    records = np.ascontiguousarray(records, dtype=np.uint8)
+    out = np.empty((ph, pw, 3), np.float32)
+    g = (C.c_uint * 4)(*gaze) if gaze is not None else None
+    lib().orc_decode_frame_blocks.restype = C.c_int
+    rc = lib().orc_decode_frame_blocks(_ptr(records), pw, ph, tbw, tbh, fg_q, bg_q, g, _ptr(out, _f32p))
+    if rc != 0:
+        raise ValueError("orc_decode_frame_blocks: bad block size")
+    return out

@@ -92,4 +92,16 @@ cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* n_launches);
 // once per device (opt-in shared memory sizes etc.)
 cudaError_t prepare_dct_kernels();
 
+// ---- decoder block path: dequantise + 8x8 IDCT + merge ------------------------------
+struct DecodeParams {
+  const uint8_t* records;        // n_frames x frame_record_bytes (772-byte records, raster order)
+  uint64_t frame_record_bytes;
+  uint32_t pw, ph;               // padded frame (multiples of 8)
+  uint32_t n_frames;
+  uint32_t fg_q, bg_q;
+  uint32_t has_gaze, gaze_x, gaze_y, gaze_w, gaze_h;
+  float* out;                    // n_frames x ph x pw x 3 interleaved BGR (16-byte aligned)
+};
+cudaError_t launch_decode(const DecodeParams& p, cudaStream_t st);
+
 }  // namespace svc

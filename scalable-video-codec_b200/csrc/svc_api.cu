@@ -2,6 +2,7 @@
 // validation, device memory/stream management and the launch sequence of the
 // three hot-path kernels.  No CPU implementation of any stage exists here: a
 // missing device or a CUDA failure is reported, never worked around.
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -338,6 +339,86 @@ int svc_encode_frame_stream(const uint8_t* bgr, uint32_t frame_w, uint32_t frame
   p.scratch_frames = 1;
   CU(launch_dct(p, st, nullptr));
   CU(cudaMemcpyAsync(out, stream.p, sbytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SVC_OK;
+}
+
+// ---- decoder block path ---------------------------------------------------------------
+
+int svc_gaze_rect(uint32_t gaze_x, uint32_t gaze_y, uint32_t max_w, uint32_t max_h, uint32_t frame_w,
+                  uint32_t frame_h, uint32_t padded_w, uint32_t padded_h, svc_rect* out) {
+  if (!out) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  if (!frame_w || !frame_h || gaze_x >= frame_w || gaze_y >= frame_h)
+    return fail(SVC_ERR_INVALID_ARG, "gaze position outside the frame");
+  // CalcWithinFrameRectFromCenter, libs/decoder.cpp:66-98
+  uint32_t half_w = (max_w + 1) / 2;
+  if (gaze_x + half_w >= frame_w) half_w = frame_w - gaze_x - 1;
+  if (gaze_x < half_w) half_w = gaze_x;
+  uint32_t half_h = (max_h + 1) / 2;
+  if (gaze_y + half_h >= frame_h) half_h = frame_h - gaze_y - 1;
+  if (gaze_y < half_h) half_h = gaze_y;
+  // scaling to the padded frame, libs/decoder.cpp:172-189 (RoundFloatToInt = std::round)
+  const float wr = (float)padded_w / (float)frame_w, hr = (float)padded_h / (float)frame_h;
+  out->x = (uint32_t)(int)roundf((float)(gaze_x - half_w) * wr);
+  out->y = (uint32_t)(int)roundf((float)(gaze_y - half_h) * hr);
+  out->w = (uint32_t)(int)roundf((float)(2 * half_w) * wr);
+  out->h = (uint32_t)(int)roundf((float)(2 * half_h) * hr);
+  return SVC_OK;
+}
+
+static int check_decode_args(uint32_t pw, uint32_t ph, uint32_t tbw, uint32_t tbh, uint32_t fg_q,
+                             uint32_t bg_q) {
+  if (fg_q == 0) return fail(SVC_ERR_INVALID_ARG, "invalid foreground quantization step: must be > 0");
+  if (bg_q == 0) return fail(SVC_ERR_INVALID_ARG, "invalid background quantization step: must be > 0");
+  if (tbw != 8 || tbh != 8)
+    return fail(SVC_ERR_UNSUPPORTED, "the decoder block path supports 8x8 transform blocks only");
+  if (!pw || !ph || pw % 8 || ph % 8) return fail(SVC_ERR_INVALID_ARG, "padded dimensions must be multiples of 8");
+  if (pw > 32768 || ph > 32768) return fail(SVC_ERR_UNSUPPORTED, "frame too large");
+  return SVC_OK;
+}
+
+int svc_decode_frames_device(int device, void* cuda_stream, const uint8_t* d_records, uint32_t n_frames,
+                             uint32_t padded_w, uint32_t padded_h, uint32_t tbw, uint32_t tbh,
+                             uint32_t fg_quant_step, uint32_t bg_quant_step, const svc_rect* gaze,
+                             float* d_out_bgr) {
+  if (!d_records || !d_out_bgr) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  int rc = check_decode_args(padded_w, padded_h, tbw, tbh, fg_quant_step, bg_quant_step);
+  if (rc) return rc;
+  if (reinterpret_cast<uintptr_t>(d_out_bgr) & 15u) return fail(SVC_ERR_INVALID_ARG, "output must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(d_records) & 3u) return fail(SVC_ERR_INVALID_ARG, "records must be 4-byte aligned");
+  rc = prepare_device(device);
+  if (rc) return rc;
+  DecodeParams p{};
+  p.records = d_records;
+  p.frame_record_bytes = (uint64_t)(padded_w / 8) * (padded_h / 8) * 772u;
+  p.pw = padded_w; p.ph = padded_h;
+  p.n_frames = n_frames;
+  p.fg_q = fg_quant_step; p.bg_q = bg_quant_step;
+  if (gaze) { p.has_gaze = 1; p.gaze_x = gaze->x; p.gaze_y = gaze->y; p.gaze_w = gaze->w; p.gaze_h = gaze->h; }
+  p.out = d_out_bgr;
+  CU(launch_decode(p, static_cast<cudaStream_t>(cuda_stream)));
+  return SVC_OK;
+}
+
+int svc_decode_frame_blocks(const uint8_t* frame_records, uint32_t padded_w, uint32_t padded_h,
+                            uint32_t tbw, uint32_t tbh, uint32_t fg_quant_step, uint32_t bg_quant_step,
+                            const svc_rect* gaze, float* out_bgr) {
+  if (!frame_records || !out_bgr) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  int rc = check_decode_args(padded_w, padded_h, tbw, tbh, fg_quant_step, bg_quant_step);
+  if (rc) return rc;
+  rc = prepare_device(g_device);
+  if (rc) return rc;
+  const size_t in_bytes = (size_t)(padded_w / 8) * (padded_h / 8) * 772u;
+  const size_t out_bytes = (size_t)padded_w * padded_h * 3 * sizeof(float);
+  DevBuf in, out;
+  CU(in.alloc(in_bytes));
+  CU(out.alloc(out_bytes));
+  cudaStream_t st = 0;
+  CU(cudaMemcpyAsync(in.p, frame_records, in_bytes, cudaMemcpyHostToDevice, st));
+  rc = svc_decode_frames_device(g_device, st, in.as<uint8_t>(), 1, padded_w, padded_h, tbw, tbh,
+                                fg_quant_step, bg_quant_step, gaze, out.as<float>());
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out_bgr, out.p, out_bytes, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return SVC_OK;
 }

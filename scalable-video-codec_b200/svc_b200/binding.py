@@ -240,6 +240,42 @@ def patch_block_types(frame_stream: np.ndarray, frame_w, frame_h, block_types, t
         C.c_uint32(mv_block_h), C.c_uint32(mv_field_w), block_types.ctypes.data_as(_u32p)))
 
 
+class _Rect(C.Structure):
+    _fields_ = [("x", C.c_uint32), ("y", C.c_uint32), ("w", C.c_uint32), ("h", C.c_uint32)]
+
+
+def gaze_rect(gaze_x, gaze_y, max_w, max_h, frame_w, frame_h, padded_w, padded_h):
+    """libs/decoder.cpp:66-98, 172-189 -> (x, y, w, h) in the padded frame."""
+    r = _Rect()
+    _check(lib().svc_gaze_rect(C.c_uint32(gaze_x), C.c_uint32(gaze_y), C.c_uint32(max_w), C.c_uint32(max_h),
+                               C.c_uint32(frame_w), C.c_uint32(frame_h), C.c_uint32(padded_w),
+                               C.c_uint32(padded_h), C.byref(r)))
+    return (r.x, r.y, r.w, r.h)
+
+
+def decode_frame_blocks(frame_records, padded_w, padded_h, fg_quant_step=1, bg_quant_step=640,
+                        gaze=None, tbw=8, tbh=8) -> np.ndarray:
+    """ParseBlock + DecodeBlock over one frame's records, libs/decoder.cpp:102-149, 191-213
+    -> (padded_h, padded_w, 3) float32 BGR."""
+    rec = _u8(frame_records)
+    out = np.empty((padded_h, padded_w, 3), np.float32)
+    g = C.byref(_Rect(*gaze)) if gaze is not None else None
+    _check(lib().svc_decode_frame_blocks(rec.ctypes.data_as(_u8p), C.c_uint32(padded_w), C.c_uint32(padded_h),
+                                         C.c_uint32(tbw), C.c_uint32(tbh), C.c_uint32(fg_quant_step),
+                                         C.c_uint32(bg_quant_step), g, out.ctypes.data_as(_f32p)))
+    return out
+
+
+def decode_frames_device(device, cuda_stream, d_records, n_frames, padded_w, padded_h, d_out,
+                         fg_quant_step=1, bg_quant_step=640, gaze=None):
+    g = C.byref(_Rect(*gaze)) if gaze is not None else None
+    _check(lib().svc_decode_frames_device(C.c_int(device), C.c_void_p(cuda_stream or None),
+                                          C.c_void_p(_addr(d_records)), C.c_uint32(n_frames),
+                                          C.c_uint32(padded_w), C.c_uint32(padded_h), C.c_uint32(8), C.c_uint32(8),
+                                          C.c_uint32(fg_quant_step), C.c_uint32(bg_quant_step), g,
+                                          C.c_void_p(_addr(d_out))))
+
+
 # ---- memory helpers -------------------------------------------------------------
 
 class PinnedBuffer:

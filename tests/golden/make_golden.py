@@ -74,7 +74,39 @@ def py_serialize(planes, btypes, w, h, tbw, tbh, mvw, mbw, mbh):
     return np.frombuffer(bytes(out), np.uint8)
 
 
+def make_decode_golden():
+    """Decoder block path (libs/decoder.cpp:102-149, 191-213) restated with numpy + cv2.idct:
+    records -> quantise (round half away from zero, float) -> cv2.idct -> merge."""
+    rng = np.random.default_rng(77)
+    pw, ph = 80, 48  # 10 x 6 blocks: a partial 32-block chunk
+    f = rng.integers(0, 256, (ph, pw, 3)).astype(np.uint8)
+    planes = cv_dct_planes(f, pw, ph, 8, 8)
+    bt = rng.integers(0, 3, (ph // 16) * (pw // 16)).astype(np.uint32)
+    st = py_serialize(planes, bt, pw, ph, 8, 8, pw // 16, 16, 16)
+    rec = st.view(np.uint32).reshape(-1, 193)
+    outs = {}
+    for name, fg, bg, gaze in (("a", 1, 640, None), ("b", 3, 40, (8, 8, 32, 16)), ("c", 7, 7, (0, 0, 80, 48))):
+        exp = np.zeros((ph, pw, 3), np.float32)
+        k = 0
+        for y in range(0, ph, 8):
+            for x in range(0, pw, 8):
+                t = rec[k, 0]
+                gazed = gaze is not None and gaze[0] <= x < gaze[0] + gaze[2] and gaze[1] <= y < gaze[1] + gaze[3]
+                q = np.float32(1 if gazed else (bg if t == 0 else fg))
+                for c in range(3):
+                    b = rec[k, 1 + 64 * c:65 + 64 * c].view(np.float32).reshape(8, 8) / q
+                    b = np.where(b >= 0, np.floor(b + np.float32(0.5)), np.ceil(b - np.float32(0.5))).astype(np.float32) * q
+                    exp[y:y + 8, x:x + 8, c] = cv2.idct(b)
+                k += 1
+        outs["out_" + name] = exp
+        outs["cfg_" + name] = np.array([fg, bg] + (list(gaze) if gaze else [0, 0, 0, 0]) + [int(gaze is not None)], np.int64)
+    np.savez_compressed(os.path.join(HERE, "decode_blocks.npz"), records=st, pw=pw, ph=ph, **outs)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "decode":
+        make_decode_golden()
+        return
     assert O.have_ref(), "build oracle/_ref first: make -C oracle"
     rng = np.random.default_rng(20260101)
 

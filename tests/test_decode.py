@@ -1,0 +1,96 @@
+"""Decoder block path: dequantise + 8x8 IDCT + merge.
+CPU: oracle vs the cv2.idct golden fixture, gaze rectangle arithmetic.
+GPU: CUDA kernel vs oracle / golden on the same record bytes, encode -> decode round trip."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+IDCT_TOL = 1e-3  # absolute, on pixel-scale values (cv2.idct itself is ~5e-5 from the exact inverse)
+
+
+def _cases(g):
+    for name in "abc":
+        cfg = g["cfg_" + name]
+        gaze = tuple(int(v) for v in cfg[2:6]) if cfg[6] else None
+        yield int(cfg[0]), int(cfg[1]), gaze, g["out_" + name]
+
+
+def test_oracle_decode_matches_cv2_golden(oracle):
+    g = load_golden("decode_blocks.npz")
+    for fg, bg, gaze, exp in _cases(g):
+        out = oracle.decode_frame_blocks(g["records"], int(g["pw"]), int(g["ph"]), fg_q=fg, bg_q=bg, gaze=gaze)
+        assert np.abs(out - exp).max() <= IDCT_TOL
+
+
+@pytest.mark.parametrize("args", [(100, 50, 64, 64, 960, 540, 960, 544), (5, 535, 64, 64, 960, 540, 960, 544),
+                                  (0, 0, 64, 64, 1920, 1080, 1920, 1088), (1919, 1079, 64, 64, 1920, 1080, 1920, 1088),
+                                  (500, 300, 31, 77, 1000, 600, 1008, 608)])
+def test_gaze_rect_matches_oracle(svc, oracle, args):
+    assert svc.gaze_rect(*args) == oracle.gaze_rect(*args)
+
+
+def test_decode_argument_validation(svc):
+    rec = np.zeros(772 * 4, np.uint8)
+    out_shape = (16, 16)
+    with pytest.raises(svc.SvcError) as e:
+        svc.decode_frame_blocks(rec, 16, 16, fg_quant_step=0)
+    assert e.value.code == 1 and "foreground quantization step" in str(e.value)
+    with pytest.raises(svc.SvcError) as e:
+        svc.decode_frame_blocks(rec, 16, 16, bg_quant_step=0)
+    assert "background quantization step" in str(e.value)
+    with pytest.raises(svc.SvcError) as e:
+        svc.decode_frame_blocks(rec, 16, 16, tbw=4, tbh=4)
+    assert e.value.code == 3
+
+
+@pytest.mark.gpu
+def test_gpu_decode_golden(gpu):
+    g = load_golden("decode_blocks.npz")
+    for fg, bg, gaze, exp in _cases(g):
+        out = gpu.decode_frame_blocks(g["records"], int(g["pw"]), int(g["ph"]), fg, bg, gaze)
+        assert np.abs(out - exp).max() <= IDCT_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pw,ph", [(1920, 1088), (960, 544), (264, 40), (8, 8), (3840, 2160)])
+@pytest.mark.parametrize("fg,bg,with_gaze", [(1, 640, False), (2, 37, True)])
+def test_gpu_decode_vs_oracle(gpu, oracle, pw, ph, fg, bg, with_gaze):
+    rng = np.random.default_rng(pw + ph + fg)
+    n = (pw // 8) * (ph // 8)
+    rec = np.empty((n, 193), np.uint32)
+    rec[:, 0] = rng.integers(0, 3, n)
+    coef = (rng.standard_normal((n, 192)) * 300).astype(np.float32)
+    coef[:, ::64] = rng.uniform(0, 2040, (n, 3)).astype(np.float32)  # DC terms
+    rec[:, 1:] = coef.view(np.uint32)
+    gaze = (pw // 4 // 8 * 8, 0, min(64, pw), min(48, ph)) if with_gaze else None
+    got = gpu.decode_frame_blocks(rec.view(np.uint8).ravel(), pw, ph, fg, bg, gaze)
+    if pw * ph > 1000 * 1000:  # the oracle on a crop of whole block rows (records are row-major)
+        rows = 16
+        exp = oracle.decode_frame_blocks(rec[: (pw // 8) * (rows // 8)].view(np.uint8).ravel(), pw, rows,
+                                         fg_q=fg, bg_q=bg, gaze=gaze)
+        assert np.abs(got[:rows] - exp).max() <= IDCT_TOL
+        tail = rec[-(pw // 8) * 2:]
+        gz = None if gaze is None else (gaze[0], 0, 0, 0)  # the last rows are outside the gaze rectangle
+        exp = oracle.decode_frame_blocks(tail.view(np.uint8).ravel(), pw, 16, fg_q=fg, bg_q=bg, gaze=gz)
+        assert np.abs(got[-16:] - exp).max() <= IDCT_TOL
+    else:
+        exp = oracle.decode_frame_blocks(rec.view(np.uint8).ravel(), pw, ph, fg_q=fg, bg_q=bg, gaze=gaze)
+        assert np.abs(got - exp).max() <= IDCT_TOL
+
+
+@pytest.mark.gpu
+def test_gpu_encode_decode_round_trip(gpu):
+    """Stream written by K3 for a frame that needs no padding, decoded with q = 1 (which still
+    rounds every coefficient to an integer, libs/decoder.cpp:140-142): the pixels return within
+    the rounding noise of 64 orthonormal coefficients (rms ~0.29, bounded by 0.5 * 8)."""
+    from svc_b200.synth import SyntheticSequence
+    w, h = 320, 176  # multiples of 16: padded == unpadded, encoder and decoder record counts agree
+    f = SyntheticSequence(w, h, 2, seed=5).frames()
+    st = gpu.encode_frame_stream(f[1], w, h)
+    dec = gpu.decode_frame_blocks(st, w, h, fg_quant_step=1, bg_quant_step=1)
+    err = np.abs(dec - f[1].astype(np.float32))
+    assert err.max() <= 4.0 and err.mean() < 0.4
+    # coarse background quantisation: still the same picture within the quantisation error
+    dec = gpu.decode_frame_blocks(st, w, h, fg_quant_step=1, bg_quant_step=16)
+    assert np.abs(dec - f[1].astype(np.float32)).mean() < 8.0
