@@ -720,6 +720,7 @@ int svc_session_create(const svc_session_config* cfg, svc_session** out) {
     // batch are placed first, so the ALU-bound motion work co-runs with the HBM-bound K3
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (getenv("SVC_MOTION_LOW_PRIORITY")) prio_hi = prio_lo;  // experiment hook
     e = cudaStreamCreateWithPriority(&s->s_aux, cudaStreamNonBlocking, prio_hi);
   }
   if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate(motion)"));
