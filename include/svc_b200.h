@@ -249,6 +249,23 @@ int svc_decode_frames_device(int device, void* cuda_stream, const uint8_t* d_rec
                              uint32_t tbw, uint32_t tbh, uint32_t fg_quant_step,
                              uint32_t bg_quant_step, const svc_rect* gaze, float* d_out_bgr);
 
+/* Stream validator: record geometry implied by a 32-byte header on the encoder side
+ * (SerializeEncodedFrame iterates the UNPADDED frame, libs/encoder.cpp:243-244) and on
+ * the decoder side (Decoder::operator() iterates the PADDED frame, libs/decoder.cpp:
+ * 191-192; the reader thread likewise, apps/decoder.cpp:66-71).  The two agree only when
+ * ceil(h/tbh) == padded_h/tbh and ceil(w/tbw) == padded_w/tbw -- true for 960x540 and
+ * 3840x2160, false for 1920x1080 (135 vs 136 block rows): a reference inconsistency that
+ * this library preserves and reports instead of hiding. */
+typedef struct svc_stream_layout {
+  uint32_t frame_count, frame_w, frame_h, padded_w, padded_h, tbw, tbh, channels;
+  uint32_t record_bytes;
+  uint64_t encoder_records_per_frame; /* what the encoder writes */
+  uint64_t decoder_records_per_frame; /* what the reference decoder will try to read */
+  uint64_t encoder_stream_bytes;      /* 32 + frame_count * encoder_records * record_bytes */
+  int32_t consistent;                 /* 1 when both conventions agree */
+} svc_stream_layout;
+int svc_stream_layout_from_header(const uint8_t header32[32], svc_stream_layout* out);
+
 /* Memory helpers so that non-CUDA hosts (ctypes, cgo, JNI) need no runtime. */
 void* svc_host_alloc(size_t bytes); /* pinned */
 void svc_host_free(void* p);

@@ -343,6 +343,24 @@ int svc_encode_frame_stream(const uint8_t* bgr, uint32_t frame_w, uint32_t frame
   return SVC_OK;
 }
 
+int svc_stream_layout_from_header(const uint8_t header32[32], svc_stream_layout* out) {
+  if (!header32 || !out) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  uint32_t h[8];
+  memcpy(h, header32, 32);  // libs/codec.hpp:8-17
+  if (!h[5] || !h[6] || !h[7] || !h[1] || !h[2]) return fail(SVC_ERR_INVALID_ARG, "malformed header");
+  svc_stream_layout L{};
+  L.frame_count = h[0]; L.frame_w = h[1]; L.frame_h = h[2];
+  L.padded_w = h[1] + h[3]; L.padded_h = h[2] + h[4];
+  L.tbw = h[5]; L.tbh = h[6]; L.channels = h[7];
+  L.record_bytes = 4 + L.channels * L.tbw * L.tbh * 4;
+  L.encoder_records_per_frame = (uint64_t)((L.frame_w + L.tbw - 1) / L.tbw) * ((L.frame_h + L.tbh - 1) / L.tbh);
+  L.decoder_records_per_frame = (uint64_t)((L.padded_w + L.tbw - 1) / L.tbw) * ((L.padded_h + L.tbh - 1) / L.tbh);
+  L.encoder_stream_bytes = 32 + (uint64_t)L.frame_count * L.encoder_records_per_frame * L.record_bytes;
+  L.consistent = L.encoder_records_per_frame == L.decoder_records_per_frame;
+  *out = L;
+  return SVC_OK;
+}
+
 // ---- decoder block path ---------------------------------------------------------------
 
 int svc_gaze_rect(uint32_t gaze_x, uint32_t gaze_y, uint32_t max_w, uint32_t max_h, uint32_t frame_w,

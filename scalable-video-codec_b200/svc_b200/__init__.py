@@ -11,7 +11,7 @@ from .binding import (  # noqa: F401
     SvcError, lib, lib_path, device_count, sad_peak, padded_dim, serialized_frame_bytes,
     write_header, EstimateMotionHierarchical, EstimateMotionHierarchical16x16Sse2,
     EstimateMotionExhaustiveSearch, y_pyramid, dct_planar, encode_frame_stream,
-    patch_block_types, gaze_rect, decode_frame_blocks, decode_frames_device, Session, SessionConfig, PinnedBuffer, DeviceBuffer,
+    patch_block_types, stream_layout, gaze_rect, decode_frame_blocks, decode_frames_device, Session, SessionConfig, PinnedBuffer, DeviceBuffer,
     STAGE_Y_PYRAMID, STAGE_HBMA, STAGE_DCT_STREAM, STAGE_PYR_DOWN,
 )
 from .shard import shard_frame_ranges, gather_streams  # noqa: F401

@@ -240,6 +240,21 @@ def patch_block_types(frame_stream: np.ndarray, frame_w, frame_h, block_types, t
         C.c_uint32(mv_block_h), C.c_uint32(mv_field_w), block_types.ctypes.data_as(_u32p)))
 
 
+class _Layout(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("frame_count", "frame_w", "frame_h", "padded_w", "padded_h", "tbw",
+                                          "tbh", "channels", "record_bytes")] + \
+               [("encoder_records_per_frame", C.c_uint64), ("decoder_records_per_frame", C.c_uint64),
+                ("encoder_stream_bytes", C.c_uint64), ("consistent", C.c_int32)]
+
+
+def stream_layout(header32) -> dict:
+    """Record geometry implied by a stream header on the encoder and on the decoder side."""
+    hdr = _u8(header32)
+    out = _Layout()
+    _check(lib().svc_stream_layout_from_header(hdr.ctypes.data_as(_u8p), C.byref(out)))
+    return {n: getattr(out, n) for n, _ in _Layout._fields_}
+
+
 class _Rect(C.Structure):
     _fields_ = [("x", C.c_uint32), ("y", C.c_uint32), ("w", C.c_uint32), ("h", C.c_uint32)]
 

@@ -107,3 +107,16 @@ def test_patch_block_types_matches_oracle_serializer(svc, oracle):
     st = ref_zero.copy()
     svc.patch_block_types(st, w, h, bt, mv_field_w=pw // 16)
     assert np.array_equal(st, ref_bt)
+
+
+def test_stream_layout_reports_the_reference_encoder_decoder_mismatch(svc):
+    # encoder iterates the unpadded frame, the reference decoder the padded one
+    l = svc.stream_layout(svc.write_header(300, 1920, 1080, 1920, 1088))
+    assert (l["encoder_records_per_frame"], l["decoder_records_per_frame"]) == (240 * 135, 240 * 136)
+    assert l["consistent"] == 0 and l["record_bytes"] == 772
+    assert l["encoder_stream_bytes"] == 32 + 299 * 240 * 135 * 772
+    for (w, h) in ((960, 540), (3840, 2160)):
+        pw, ph = svc.padded_dim(w, 16, 4), svc.padded_dim(h, 16, 4)
+        assert svc.stream_layout(svc.write_header(30, w, h, pw, ph))["consistent"] == 1
+    with pytest.raises(svc.SvcError):
+        svc.stream_layout(np.zeros(32, np.uint8))
