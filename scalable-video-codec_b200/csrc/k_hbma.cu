@@ -563,6 +563,150 @@ hbma_window_kernel(const __grid_constant__ HbmaWindowMaps maps, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------
+// Window kernel, warp-per-block variant (mid ranges, r <= ~16): the same per-level TMA
+// window + item scheme as hbma_window_kernel, but every WARP owns one motion block, with
+// its own shared-memory slice and its own mbarrier, so nothing in the level loop is
+// block-wide: 8 independent level chains per CTA (up to 64 per SM) hide the TMA round
+// trips that dominate when a window only holds a few dozen items.
+// ---------------------------------------------------------------------------
+constexpr int kWinWarps = 8;
+
+template <int B>
+__device__ __forceinline__ void window_level_warp(const uint8_t* sW, const int PW, const uint8_t* sA,
+                                                  uint16_t* sS, const bool top, const int ncx,
+                                                  const int ncy, const int sx_base, const int a_off,
+                                                  uint32_t& best_key, bool& any_viol) {
+  constexpr int NDY = 8;
+  const int lane = threadIdx.x & 31;
+  const int nch = (ncy + NDY - 1) / NDY;
+  const int n_items = ncx * nch;
+  uint32_t key = 0xffffffffu;
+  for (int item = lane; item < n_items; item += 32) {
+    const int c = item / ncx, dx = item - c * ncx;
+    const int dy0 = c * NDY, ndy = min(NDY, ncy - dy0);
+    uint32_t acc[NDY];
+#pragma unroll
+    for (int i = 0; i < NDY; ++i) acc[i] = 0;
+    sad_column<B, NDY, false>(sW + dy0 * PW, PW, sx_base + dx, sA + a_off, 16, acc, 0);
+#pragma unroll
+    for (int i = 0; i < NDY; ++i) {
+      if (i < ndy) {
+        const uint32_t idx = (uint32_t)((dy0 + i) * ncx + dx);
+        if (top) {
+          sS[idx] = (uint16_t)acc[i];
+          key = min(key, (acc[i] << 16) | (0xffffu - idx));
+        } else {
+          key = min(key, (acc[i] << 16) | idx);
+        }
+      }
+    }
+  }
+  best_key = __reduce_min_sync(0xffffffffu, key);
+  bool viol = false;
+  if (top) {
+    __syncwarp();  // sS complete
+    const int n = ncx * ncy;
+    for (int i = lane + 1; i < n; i += 32) viol |= sS[i] > sS[i - 1];
+  }
+  any_viol = __any_sync(0xffffffffu, viol);
+}
+
+__global__ void __launch_bounds__(kWinWarps * 32)
+hbma_window_warp_kernel(const __grid_constant__ HbmaWindowMaps maps, const __grid_constant__ HbmaParams p,
+                        const __grid_constant__ WinGeom g) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[kWinWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t per_frame = p.mvw * p.mvh;
+  const uint64_t gb = (uint64_t)blockIdx.x * kWinWarps + wid;
+  if (gb >= (uint64_t)per_frame * p.n_frames) return;  // whole warp leaves; no block-wide sync below
+  const uint32_t f = (uint32_t)(gb / per_frame), bi = (uint32_t)(gb % per_frame);
+  const int bx = (int)(bi % p.mvw), by = (int)(bi / p.mvw);
+  const int r = (int)p.r, L = (int)p.lay.levels;
+  uint8_t* base = smem + (size_t)wid * g.smem_bytes;  // per-warp slice
+  uint8_t* sW = base;
+  uint8_t* sA = base + g.off_anchor;
+  uint16_t* sS = reinterpret_cast<uint16_t*>(base + g.off_sads);
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bars[wid]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  int mx = 0, my = 0;
+  float cur = FLT_MAX;
+  uint32_t parity = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const bool top = (l == L - 1);
+    const int B = 16 >> l;
+    const int fw = (int)p.lay.w[l], fh = (int)p.lay.h[l];
+    if (!top) { mx *= 2; my *= 2; }
+    const int ax = bx * B, ay = by * B;
+    const int cx = ax + mx, cy = ay + my;
+    const int x0 = max(0, cx - r), x1 = min(fw - B + 1, cx + r + 1);
+    const int y0 = max(0, cy - r), y1 = min(fh - B + 1, cy + r + 1);
+    const int ncx = x1 - x0, ncy = y1 - y0;
+    const int wx = x0 & ~15;
+    __syncwarp();  // every lane is done with the previous level's window
+    if (lane == 0) {
+      if (p.counters) {
+        atomicAdd(p.counters, (unsigned long long)(ncx * ncy));
+        atomicAdd(p.counters + 1, (unsigned long long)(ncx * ncy) * B * B);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                   "r"(g.box_w[l] * g.box_h[l] + 16u * (uint32_t)B) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(sW)), "l"(&maps.t[l]), "r"(wx), "r"(y0), "r"((int)f),
+          "r"(bar_addr) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(sA)), "l"(&maps.a[l]), "r"(ax & ~15), "r"(ay),
+          "r"((int)f + 1), "r"(bar_addr) : "memory");
+    }
+    {
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar_addr), "r"(parity) : "memory");
+      }
+      parity ^= 1u;
+    }
+    uint32_t best;
+    bool any_viol;
+    const int PW = (int)g.box_w[l], sxb = x0 - wx, aoff = ax & 15;
+    switch (B) {
+      case 16: window_level_warp<16>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      case 8:  window_level_warp<8>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      case 4:  window_level_warp<4>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      case 2:  window_level_warp<2>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      default: window_level_warp<1>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+    }
+    const float m = (float)(best >> 16) * (1.0f / (float)(B * B));
+    const int idx = top ? (int)(0xffffu - (best & 0xffffu)) : (int)(best & 0xffffu);
+    const int nmx = x0 + idx % ncx - ax, nmy = y0 + idx / ncx - ay;
+    if (top) {
+      cur = m;
+      mx = any_viol ? nmx : 0;
+      my = any_viol ? nmy : 0;
+    } else if (m < cur) {
+      cur = m;
+      mx = nmx;
+      my = nmy;
+    }
+  }
+  if (lane == 0) {
+    const uint64_t o = (uint64_t)f * per_frame + bi;
+    if (p.mv) p.mv[o] = make_float2((float)mx, (float)my);
+    if (p.mad) p.mad[o] = cur;
+  }
+}
+
 // ---- host side: tensor maps + dispatch -----------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -660,6 +804,17 @@ static bool try_launch_window(const HbmaParams& p, cudaStream_t st, cudaError_t*
   g.off_sads = g.off_anchor + 256;
   g.smem_bytes = g.off_sads + (((2 * r + 1) * (2 * r + 1) * 2 + 127) & ~127u);
   if (g.smem_bytes > 200 * 1024) return false;
+  static const bool no_warp = getenv("SVC_HBMA_NO_WARP_WINDOW") != nullptr;  // experiment hook
+  if (g.smem_bytes <= 7 * 1024 && !no_warp) {
+    // small windows: one warp per motion block, 8 blocks per CTA
+    const uint32_t ctas = (uint32_t)((n_ctas + kWinWarps - 1) / kWinWarps);
+    *err = cudaFuncSetAttribute(hbma_window_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(g.smem_bytes * kWinWarps));
+    if (*err != cudaSuccess) return true;
+    hbma_window_warp_kernel<<<ctas, kWinWarps * 32, g.smem_bytes * kWinWarps, st>>>(maps, p, g);
+    *err = cudaGetLastError();
+    return true;
+  }
   const uint32_t items = (2 * r + 1) * ((2 * r + 1 + 7) / 8);
   const uint32_t threads = items <= 64 ? 64 : (items <= 160 ? 128 : 256);
   *err = cudaFuncSetAttribute(hbma_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
