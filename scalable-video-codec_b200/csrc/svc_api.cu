@@ -79,12 +79,63 @@ int check_hbma_args(uint32_t levels, uint32_t fw, uint32_t fh, uint32_t range,
   return SVC_OK;
 }
 
+// Device scratch of the stateless entry points: a small per-thread, per-device cache of
+// grow-only allocations, so that a host calling e.g. svc_estimate_motion_hierarchical once
+// per frame (drop-in 1) does not pay cudaMalloc/cudaFree on every call.
+// A DevBuf borrows one cache slot for its lifetime (calls on one thread do not nest).
+struct ScratchSlot {
+  void* p = nullptr;
+  size_t cap = 0;
+  int device = -1;
+  bool busy = false;
+};
+constexpr int kScratchSlots = 6;
+struct ScratchCache {
+  ScratchSlot slot[kScratchSlots];
+  ~ScratchCache() {
+    for (auto& s : slot)
+      if (s.p && cudaSetDevice(s.device) == cudaSuccess) cudaFree(s.p);
+  }
+};
+thread_local ScratchCache g_scratch;
+
 struct DevBuf {
   void* p = nullptr;
+  ScratchSlot* slot = nullptr;
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (slot) slot->busy = false;
   }
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+  cudaError_t alloc(size_t n) {
+    if (n == 0) n = 1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    ScratchSlot* pick = nullptr;
+    for (auto& s : g_scratch.slot)  // smallest free slot on this device that is large enough
+      if (!s.busy && s.device == dev && s.cap >= n && (!pick || s.cap < pick->cap)) pick = &s;
+    if (!pick) {
+      for (auto& s : g_scratch.slot)  // else recycle the smallest free slot (or an empty one)
+        if (!s.busy && (!pick || s.cap < pick->cap)) pick = &s;
+      if (!pick) return cudaErrorMemoryAllocation;
+      if (pick->p) {
+        if (cudaSetDevice(pick->device) == cudaSuccess) cudaFree(pick->p);
+        cudaSetDevice(dev);
+        pick->p = nullptr;
+        pick->cap = 0;
+      }
+      e = cudaMalloc(&pick->p, n);
+      if (e != cudaSuccess) {
+        pick->p = nullptr;
+        return e;
+      }
+      pick->cap = n;
+      pick->device = dev;
+    }
+    pick->busy = true;
+    slot = pick;
+    p = pick->p;
+    return cudaSuccess;
+  }
   template <class T>
   T* as() { return static_cast<T*>(p); }
 };
