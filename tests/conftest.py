@@ -24,8 +24,14 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def svc():
+    import subprocess
+
     import svc_b200
-    svc_b200.lib()  # hard failure if the CUDA library was not built
+    if not os.path.exists(svc_b200.lib_path()):
+        # fresh checkout (built artefacts are git-ignored): build the product first
+        subprocess.run(["make", "-C", os.path.join(ROOT, "scalable-video-codec_b200"), "-j4"], check=True,
+                       stdout=subprocess.DEVNULL)
+    svc_b200.lib()  # hard failure if the CUDA library cannot be loaded
     return svc_b200
 
 
