@@ -313,6 +313,45 @@ def test_device_work_counters_match_oracle(gpu, oracle, R, L):
     assert gpu.sad_peak(0) > 1e12  # > 1 T byte-absdiff/s on any B200
 
 
+def test_session_output_subsets_reset_and_concurrent_sessions(gpu, oracle):
+    """NULL outputs skip their stage, reset() restarts the sequence, and two sessions driven
+    from two host threads on one GPU do not disturb each other."""
+    import threading
+    w, h, n = 320, 180, 7
+    frames = SyntheticSequence(w, h, n, seed=77).frames()
+    pw, ph = gpu.padded_dim(w, 16, 4), gpu.padded_dim(h, 16, 4)
+    pyr = [oracle.y_pyramid(f, pw, ph, 4) for f in frames]
+    emv = [oracle.hbma(pyr[i - 1], pyr[i], 8)[0] for i in range(1, n)]
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, max_batch=3)) as s:
+        mv, mad, st = s.encode(frames, want_mad=False, want_stream=False)
+        assert mad is None and st is None and all(np.array_equal(mv[i], emv[i]) for i in range(n - 1))
+        s.reset()
+        mv, mad, st = s.encode(frames, want_mv=False, want_mad=False)
+        assert mv is None and st.shape == (n - 1, s.frame_stream_bytes)
+        exp = oracle.serialize_frame(oracle.dct_planar(frames[3], pw, ph), None, w, h, 8, 8, pw // 16, 16, 16)
+        assert np.abs(st[2].view(np.float32) - exp.view(np.float32)).max() <= DCT_TOL
+        s.reset()
+        mv2, _, _ = s.encode(frames[2:])  # a fresh sequence starting at frame 2
+        assert mv2.shape[0] == n - 3 and np.array_equal(mv2[0], emv[2])
+    results = {}
+
+    def run(tag, seed):
+        fr = SyntheticSequence(w, h, n, seed=seed).frames()
+        with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, max_batch=2)) as ss:
+            for _ in range(3):
+                ss.reset()
+                results[tag] = (fr, ss.encode(fr)[0])
+
+    th = [threading.Thread(target=run, args=(k, 100 + k)) for k in range(2)]
+    [t_.start() for t_ in th]
+    [t_.join() for t_ in th]
+    for k in range(2):
+        fr, mv = results[k]
+        p = [oracle.y_pyramid(f, pw, ph, 4) for f in fr]
+        for i in range(1, n):
+            assert np.array_equal(mv[i - 1], oracle.hbma(p[i - 1], p[i], 8)[0])
+
+
 def test_stage_entry_points(gpu, oracle):
     w, h, n = 320, 180, 3
     seq = SyntheticSequence(w, h, n, seed=8)
