@@ -65,6 +65,34 @@ bgr_to_y_kernel(const uint8_t* __restrict__ bgr, uint32_t w, uint32_t h,
   *reinterpret_cast<uint32_t*>(dst) = out;
 }
 
+// 16 pixels per thread: three 128-bit loads, one 128-bit store (w % 16 == 0, 16-byte aligned
+// frames).  Y via two 16x8-bit dot products per pixel (dp2a), as in the fused K3 path.
+__device__ __forceinline__ uint32_t luma4(uint32_t w0, uint32_t w1, uint32_t w2) {
+  auto y = [](uint32_t px) {
+    return __dp2a_hi(4899u, px, __dp2a_lo(1868u | (9617u << 16), px, 8192u)) >> 14;
+  };
+  return y(w0) | (y(__funnelshift_r(w0, w1, 24)) << 8) | (y(__funnelshift_r(w1, w2, 16)) << 16) |
+         (y(w2 >> 8) << 24);
+}
+
+__global__ void __launch_bounds__(128)
+bgr_to_y16_kernel(const uint8_t* __restrict__ bgr, uint32_t w, uint32_t h, uint8_t* __restrict__ pyr,
+                  uint64_t slot_bytes, uint32_t first_slot, uint32_t pitch, uint32_t pw) {
+  const uint32_t x16 = (blockIdx.x * blockDim.x + threadIdx.x) * 16u;
+  const uint32_t y = blockIdx.y, f = blockIdx.z;
+  if (x16 >= pw) return;
+  uint4 out = make_uint4(0, 0, 0, 0);
+  if (y < h && x16 < w) {  // w % 16 == 0: the group is entirely inside the frame
+    const uint4* p = reinterpret_cast<const uint4*>(bgr + (((uint64_t)f * h + y) * w + x16) * 3u);
+    const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    out.x = luma4(a.x, a.y, a.z);
+    out.y = luma4(a.w, b.x, b.y);
+    out.z = luma4(b.z, b.w, c.x);
+    out.w = luma4(c.y, c.z, c.w);
+  }
+  *reinterpret_cast<uint4*>(pyr + (uint64_t)(first_slot + f) * slot_bytes + (uint64_t)y * pitch + x16) = out;
+}
+
 cudaError_t launch_bgr_to_y(const uint8_t* d_bgr, uint32_t w, uint32_t h,
                             uint8_t* d_pyr, const PyrLayout& lay,
                             uint32_t first_slot, uint32_t n_frames,
@@ -72,6 +100,13 @@ cudaError_t launch_bgr_to_y(const uint8_t* d_bgr, uint32_t w, uint32_t h,
   if (n_frames == 0) return cudaSuccess;
   const uint32_t pw = lay.w[0], ph = lay.h[0];
   dim3 block(128);
+  if (w % 16 == 0 && (reinterpret_cast<uintptr_t>(d_bgr) & 15) == 0) {
+    // level-0 pitch is a multiple of 128: a 16-byte store of the last group stays inside it
+    dim3 grid((((pw + 15) / 16) + 127) / 128, ph, n_frames);
+    bgr_to_y16_kernel<<<grid, block, 0, st>>>(d_bgr, w, h, d_pyr + lay.off[0], lay.slot_bytes,
+                                               first_slot, lay.pitch[0], (pw + 15) & ~15u);
+    return cudaGetLastError();
+  }
   dim3 grid((pw / 4 + 127) / 128, ph, n_frames);
   // level-0 pitch is a multiple of 128 and pw a multiple of 2^(levels-1); the
   // 4-byte store of a partial last group stays inside the pitch.
