@@ -289,19 +289,21 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
         dw, dh, lay.pitch[l + 1]);
     return cudaGetLastError();
   }
-  static const char* env_thr = getenv("SVC_PYR_BIG_MPIX");  // tuning hook
+  static const char* env_thr = getenv("SVC_PYR_BIG_MPIX");  // tuning hooks
+  static const char* env_rpt = getenv("SVC_PYR_BIG_RPT");
   const uint64_t thr = env_thr ? (uint64_t)atoll(env_thr) << 20 : (8ull << 20);
   const bool big = (uint64_t)dw * dh * n_frames >= thr;
-  const uint32_t tile_h = big ? 32 : 8;
+  const int rpt = big ? (env_rpt ? atoi(env_rpt) : 8) : 2;
+  const uint32_t tile_h = 4u * (uint32_t)rpt;
   dim3 grid((dw + kPdTileW - 1) / kPdTileW, (dh + tile_h - 1) / tile_h, n_frames);
-  if (big)
-    pyr_down_kernel<8><<<grid, block, 0, st>>>(d_pyr, lay.slot_bytes, first_slot, lay.off[l], lay.w[l],
-                                               lay.h[l], lay.pitch[l], lay.off[l + 1], dw, dh,
-                                               lay.pitch[l + 1]);
-  else
-    pyr_down_kernel<2><<<grid, block, 0, st>>>(d_pyr, lay.slot_bytes, first_slot, lay.off[l], lay.w[l],
-                                               lay.h[l], lay.pitch[l], lay.off[l + 1], dw, dh,
-                                               lay.pitch[l + 1]);
+#define SVC_PYR_LAUNCH(RPT)                                                                          \
+  pyr_down_kernel<RPT><<<grid, block, 0, st>>>(d_pyr, lay.slot_bytes, first_slot, lay.off[l], lay.w[l], \
+                                               lay.h[l], lay.pitch[l], lay.off[l + 1], dw, dh,       \
+                                               lay.pitch[l + 1])
+  if (rpt == 8) SVC_PYR_LAUNCH(8);
+  else if (rpt == 4) SVC_PYR_LAUNCH(4);
+  else SVC_PYR_LAUNCH(2);
+#undef SVC_PYR_LAUNCH
   return cudaGetLastError();
 }
 
