@@ -339,7 +339,8 @@ def run_ours(a):
         P = sess.padded_w * sess.padded_h
         fused_y = (W == sess.padded_w)                     # K3 also writes the level-0 luma
         dct_bytes = B * (fin + fst + (P if fused_y else 0))  # read BGR once, write records (+Y) once
-        pyr_bytes = B * sum(P >> (2 * l) for l in range(a.levels))  # read L0..L(n-2), write L1..L(n-1) ~ sum
+        pyr_bytes = B * (sum(P >> (2 * l) for l in range(a.levels - 1)) +      # read levels 0..L-2
+                         sum(P >> (2 * l) for l in range(1, a.levels)))      # write levels 1..L-1
         hbma_bytes = B * (2 * sum(P >> (2 * l) for l in range(a.levels)) + mvn * 12)
         stages = {
             "dct_stream_y": {"ms_per_launch": ms_dct, "frames_per_launch": B,
