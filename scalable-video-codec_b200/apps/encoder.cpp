@@ -15,14 +15,19 @@
 #include <string>
 #include <thread>
 
+#include <vector>
+
 #include "../host/encoder.hpp"
+#include "../host/sharded.hpp"
 
 static void usage() {
   std::fprintf(stderr,
                "usage: svc_encoder --width W --height H [--frames N] [--mv-search-range R]\n"
                "                   [--pyr-lvl-count L] [--mv-block-w B] [--mv-block-h B]\n"
                "                   [--transform-block-w T] [--transform-block-h T] [--device D]\n"
-               "                   [--batch K] [--verbose 0|1] <raw-bgr-file | ->\n");
+               "                   [--batch K] [--verbose 0|1] <raw-bgr-file | ->\n"
+               "       svc_encoder ... --devices 0,1,2,3 --out stream.svc <raw-bgr-file>\n"
+               "         (frame-range sharded over several GPUs, one host thread per GPU)\n");
 }
 
 int main(int argc, char** argv) {
@@ -30,6 +35,8 @@ int main(int argc, char** argv) {
   unsigned width = 0, height = 0, frames = 0;
   int verbose = 1;
   const char* path = nullptr;
+  const char* out_path = nullptr;
+  std::vector<int> devices;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto val = [&](unsigned& out) {
@@ -49,6 +56,14 @@ int main(int argc, char** argv) {
     else if (a == "--batch") val(cfg.max_batch);
     else if (a == "--device") { val(tmp); cfg.device = (int)tmp; }
     else if (a == "--verbose") { val(tmp); verbose = (int)tmp; }
+    else if (a == "--out") { if (i + 1 >= argc) { usage(); return EXIT_FAILURE; } out_path = argv[++i]; }
+    else if (a == "--devices") {
+      if (i + 1 >= argc) { usage(); return EXIT_FAILURE; }
+      for (const char* q = argv[++i]; *q;) {
+        devices.push_back((int)std::strtol(q, const_cast<char**>(&q), 10));
+        if (*q == ',') ++q;
+      }
+    }
     else if (a == "-" || a[0] != '-') path = argv[i];
     else { usage(); return EXIT_FAILURE; }
   }
@@ -68,6 +83,26 @@ int main(int argc, char** argv) {
   }
   if (!frames) { std::fprintf(stderr, "--frames is required when reading stdin\n"); return EXIT_FAILURE; }
   if (verbose) std::fprintf(stderr, "frame width: %u\nframe height: %u\nframe count: %u\n", width, height, frames);
+
+  if (!devices.empty()) {  // sharded multi-GPU mode: seekable input, file output
+    if (in == stdin || !out_path) {
+      std::fprintf(stderr, "--devices needs a seekable input file and --out\n");
+      return EXIT_FAILURE;
+    }
+    std::fclose(in);
+    try {
+      const svc::ShardedStats s = svc::EncodeFileSharded(cfg, svc::VideoProperties{width, height, frames}, path,
+                                                         out_path, devices);
+      if (verbose)
+        std::fprintf(stderr, "encoded %llu frames on %zu device(s) in %.3f s (%.1f frames/s)\n",
+                     (unsigned long long)s.frames_encoded, devices.size(), s.seconds,
+                     s.seconds > 0 ? s.frames_encoded / s.seconds : 0.0);
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "svc_encoder: %s\n", e.what());
+      return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+  }
 
   svc::BoundedQueue<svc::Frame> in_queue(10);
   svc::BoundedQueue<svc::Bytes> out_queue(10);

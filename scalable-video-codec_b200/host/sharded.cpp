@@ -1,0 +1,144 @@
+// sharded.cpp -- see sharded.hpp.
+#include "sharded.hpp"
+
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <exception>
+#include <thread>
+
+#include "../../include/svc_b200.h"
+
+namespace svc {
+
+std::vector<ShardRange> ShardFrameRanges(uint n_input_frames, uint world) {
+  std::vector<ShardRange> out;
+  const uint n_enc = n_input_frames ? n_input_frames - 1 : 0;
+  const uint base = world ? n_enc / world : 0, rem = world ? n_enc % world : 0;
+  uint t = 1;
+  for (uint r = 0; r < world; ++r) {
+    const uint k = base + (r < rem ? 1 : 0);
+    if (k == 0) out.push_back({t - 1, t - 1, t, t});
+    else out.push_back({t - 1, t + k, t, t + k});
+    t += k;
+  }
+  return out;
+}
+
+namespace {
+
+struct Pinned {
+  void* p = nullptr;
+  explicit Pinned(size_t n) : p(svc_host_alloc(n)) {
+    if (!p) throw Error(SVC_ERR_CUDA, "pinned allocation failed");
+  }
+  ~Pinned() { svc_host_free(p); }
+};
+
+void check(int rc) {
+  if (rc != SVC_OK) throw Error(rc, svc_last_error());
+}
+
+void pwrite_all(int fd, const uchar* p, size_t n, uint64_t off) {
+  while (n) {
+    const ssize_t w = ::pwrite(fd, p, n, (off_t)off);
+    if (w <= 0) throw Error(SVC_ERR_STATE, "Failed to write bytes.");
+    p += w;
+    n -= (size_t)w;
+    off += (uint64_t)w;
+  }
+}
+
+void run_shard(const EncoderConfig& cfg, const VideoProperties& vp, const std::string& in_path, int out_fd,
+               int device, ShardRange r, const BlockTypeFn& classify, uint64_t* encoded) {
+  if (r.enc_hi <= r.enc_lo) return;
+  svc_session_config c{};
+  c.struct_size = sizeof(c);
+  c.frame_w = vp.frame_w; c.frame_h = vp.frame_h;
+  c.mv_block_w = cfg.mv_block_w; c.mv_block_h = cfg.mv_block_h;
+  c.mv_search_range = cfg.mv_search_range; c.pyr_lvl_count = cfg.pyr_lvl_count;
+  c.transform_block_w = cfg.transform_block_w; c.transform_block_h = cfg.transform_block_h;
+  c.device = device; c.max_batch = cfg.max_batch;
+  svc_session* s = nullptr;
+  check(svc_session_create(&c, &s));
+  struct Guard { svc_session* s; ~Guard() { svc_session_destroy(s); } } guard{s};
+  svc_session_info info{};
+  check(svc_session_info_get(s, &info));
+  const size_t B = info.max_batch, mvn = (size_t)info.mv_field_w * info.mv_field_h;
+  Pinned h_in(B * info.frame_in_bytes), h_st(B * info.frame_stream_bytes), h_mv(B * mvn * 8), h_mad(B * mvn * 4);
+  std::vector<uint> bt(mvn);
+  FILE* in = std::fopen(in_path.c_str(), "rb");
+  if (!in) throw Error(SVC_ERR_INVALID_ARG, "Failed to open " + in_path);
+  struct FGuard { FILE* f; ~FGuard() { std::fclose(f); } } fguard{in};
+  if (fseeko(in, (off_t)((uint64_t)r.in_lo * info.frame_in_bytes), SEEK_SET) != 0)
+    throw Error(SVC_ERR_INVALID_ARG, "seek failed");
+  uint next_in = r.in_lo, next_enc = r.enc_lo;
+  while (next_in < r.in_hi) {
+    const uint n = (uint)std::min<size_t>(B, r.in_hi - next_in);
+    if (std::fread(h_in.p, info.frame_in_bytes, n, in) != n) throw Error(SVC_ERR_INVALID_ARG, "short read");
+    uint n_enc = 0;
+    check(svc_session_encode(s, static_cast<const uint8_t*>(h_in.p), n, static_cast<float*>(h_mv.p),
+                             static_cast<float*>(h_mad.p), static_cast<uint8_t*>(h_st.p), nullptr, &n_enc));
+    for (uint i = 0; i < n_enc; ++i) {
+      uchar* rec = static_cast<uchar*>(h_st.p) + (size_t)i * info.frame_stream_bytes;
+      if (classify) {
+        std::fill(bt.begin(), bt.end(), 0u);
+        classify(reinterpret_cast<const Vec2f*>(static_cast<float*>(h_mv.p) + (size_t)i * mvn * 2),
+                 static_cast<float*>(h_mad.p) + (size_t)i * mvn, info.mv_field_w, info.mv_field_h, bt.data());
+        check(svc_patch_block_types(rec, vp.frame_w, vp.frame_h, cfg.transform_block_w, cfg.transform_block_h, 3,
+                                    cfg.mv_block_w, cfg.mv_block_h, info.mv_field_w, bt.data()));
+      }
+    }
+    // encoded frame t (anchor = input frame t) lives at 32 + (t-1) * frame_stream_bytes
+    pwrite_all(out_fd, static_cast<uchar*>(h_st.p), (size_t)n_enc * info.frame_stream_bytes,
+               32 + (uint64_t)(next_enc - 1) * info.frame_stream_bytes);
+    next_in += n;
+    next_enc += n_enc;
+    *encoded += n_enc;
+  }
+}
+
+}  // namespace
+
+ShardedStats EncodeFileSharded(const EncoderConfig& cfg, const VideoProperties& vidprops,
+                               const std::string& in_path, const std::string& out_path,
+                               const std::vector<int>& devices, BlockTypeFn classify) {
+  if (devices.empty()) throw Error(SVC_ERR_INVALID_ARG, "no devices");
+  const Status st = Validate(cfg);
+  if (st.code != ErrorCode::kOk) throw Error(SVC_ERR_INVALID_ARG, st.message);
+  const uint pw = svc_padded_dim(vidprops.frame_w, cfg.mv_block_w, cfg.pyr_lvl_count);
+  const uint ph = svc_padded_dim(vidprops.frame_h, cfg.mv_block_h, cfg.pyr_lvl_count);
+  const int fd = ::open(out_path.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+  if (fd < 0) throw Error(SVC_ERR_INVALID_ARG, "Failed to open " + out_path);
+  struct FdGuard { int fd; ~FdGuard() { ::close(fd); } } fdg{fd};
+  uchar hdr[32];
+  check(svc_write_header(vidprops.frame_count, vidprops.frame_w, vidprops.frame_h, pw, ph,
+                         cfg.transform_block_w, cfg.transform_block_h, 3, hdr));
+  pwrite_all(fd, hdr, 32, 0);
+  const auto ranges = ShardFrameRanges(vidprops.frame_count, (uint)devices.size());
+  std::vector<std::thread> threads;
+  std::vector<std::exception_ptr> errors(devices.size());
+  std::vector<uint64_t> encoded(devices.size(), 0);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (size_t g = 0; g < devices.size(); ++g)
+    threads.emplace_back([&, g] {
+      try {
+        run_shard(cfg, vidprops, in_path, fd, devices[g], ranges[g], classify, &encoded[g]);
+      } catch (...) {
+        errors[g] = std::current_exception();
+      }
+    });
+  for (auto& t : threads) t.join();
+  ShardedStats stats;
+  stats.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (auto& e : errors)
+    if (e) std::rethrow_exception(e);
+  for (auto n : encoded) stats.frames_encoded += n;
+  return stats;
+}
+
+}  // namespace svc

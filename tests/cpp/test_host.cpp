@@ -10,6 +10,7 @@
 
 #include "../../scalable-video-codec_b200/host/encoder.hpp"
 #include "../../scalable-video-codec_b200/host/motion.hpp"
+#include "../../scalable-video-codec_b200/host/sharded.hpp"
 #include "../../include/svc_b200.h"
 
 extern "C" {
@@ -74,6 +75,19 @@ int main(int argc, char** argv) {
     c.transform_block_w = 32;
     CHECK(svc::Validate(c).message.find("transform block width must be <= mv block width") != std::string::npos);
   }
+  // ---- frame-range sharding: partition of the encoded frames, one overlap frame -------------
+  for (uint n : {0u, 1u, 2u, 5u, 300u, 601u})
+    for (uint world : {1u, 2u, 3u, 8u}) {
+      const auto r = svc::ShardFrameRanges(n, world);
+      CHECK(r.size() == world);
+      uint next = 1;
+      for (const auto& s : r) {
+        CHECK(s.enc_lo == next && s.enc_hi >= s.enc_lo);
+        if (s.enc_hi > s.enc_lo) CHECK(s.in_lo == s.enc_lo - 1 && s.in_hi == s.enc_hi);
+        next = s.enc_hi;
+      }
+      CHECK(next == (n ? n : 1));
+    }
   int ndev = 0;
   svc_device_count(&ndev);
   if (no_gpu || ndev == 0) {

@@ -73,3 +73,27 @@ def test_encoder_app_stream_matches_oracle(gpu, oracle, tmp_path):
         e = exp.view(np.uint32).reshape(-1, 193)
         assert not g[:, 0].any()
         assert np.abs(g[:, 1:].view(np.float32) - e[:, 1:].view(np.float32)).max() <= 1e-3
+
+
+@pytest.mark.gpu
+def test_encoder_app_sharded_output_is_identical_to_single_device(gpu, tmp_path):
+    """Frame-range sharding over several sessions (here: the same GPU listed 1, 2 and 3 times)
+    must give byte-identical streams, and the same bytes as the streaming (stdout) mode."""
+    import numpy as np
+    from svc_b200.synth import SyntheticSequence
+    _build_app()
+    w, h, n = 320, 180, 11
+    raw = tmp_path / "in.bgr"
+    raw.write_bytes(SyntheticSequence(w, h, n, seed=41).frames().tobytes())
+    outs = []
+    for devs in ("0", "0,0", "0,0,0"):
+        out = tmp_path / ("out_%d.svc" % len(devs))
+        r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "4", "--verbose", "0",
+                            "--devices", devs, "--out", str(out), str(raw)], capture_output=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(out.read_bytes())
+    r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "4", "--verbose", "0", str(raw)],
+                       capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert len(outs[0]) == 32 + (n - 1) * gpu.serialized_frame_bytes(w, h)
+    assert outs[0] == outs[1] == outs[2] == r.stdout
