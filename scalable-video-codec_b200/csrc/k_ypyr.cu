@@ -10,6 +10,7 @@
 //                                                      (sum + 128) >> 8,
 //                                                      BORDER_REFLECT_101
 // All arithmetic is integer and bit-exact with OpenCV's 8-bit paths.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -126,8 +127,8 @@ cudaError_t launch_bgr_to_y(const uint8_t* d_bgr, uint32_t w, uint32_t h,
 //
 // A CTA of 128 threads produces a 128 x 32 tile of the destination level.  The
 // (2*128+32) x (2*32+3) source region is staged in shared memory once with
-// cv::borderInterpolate(BORDER_REFLECT_101) applied at load time (128-bit loads
-// for chunks inside the image, byte loads on the borders), so the arithmetic
+// cv::borderInterpolate(BORDER_REFLECT_101) applied at load time (one TMA bulk copy
+// per tile row -- SASS UBLKCP -- plus byte patches on the borders), so the arithmetic
 // below never sees a border.  Each thread then owns 4 output columns x 8 output
 // rows: it walks the 19 source rows of its strip once, forms the four
 // horizontal [1 4 6 4 1] sums of a row with packed-byte dot products (dp4a)
@@ -153,65 +154,85 @@ __device__ __forceinline__ int reflect101_near(int p, int len) {
   return min(max(p, 0), len - 1);
 }
 
-constexpr int kPdTileW = 128;                             // destination tile width
-constexpr int kPdSrcW = 2 * kPdTileW + 32;                 // 288: cols 2*x0-16 .. 2*x0+271
-constexpr int kPdChunks = kPdSrcW / 16;                    // 18 x 16-byte chunks per row
+constexpr int kPdTileW = 112;                             // destination tile width (28 lanes x 4)
+constexpr int kPdSrcW = 2 * kPdTileW + 32;                 // 256: cols 2*x0-16 .. 2*x0+239 = the TMA box width
 
 // kRpt = destination rows per thread (tile height = 4 * kRpt).  8 for the big
 // level-0 -> 1 launch; 2 for the small upper levels, where the launch is bound
 // by the latency of one CTA rather than by throughput.
+//
+// Staging: ONE TMA tensor load per CTA (cp.async.bulk.tensor.3d, box 256 x (8*kRpt+3) bytes
+// of the source level, out-of-image bytes zero-filled) completing on an mbarrier.  CTAs on
+// the image border then rebuild BORDER_REFLECT_101 inside shared memory: whole rows first
+// (row -1 <- row 1, ...), then the few border columns of every row.
 template <int kRpt>
 __global__ void __launch_bounds__(128)
-pyr_down_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t first_slot,
-                uint64_t src_off, uint32_t sw, uint32_t sh, uint32_t spitch,
+pyr_down_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restrict__ pyr,
+                uint64_t slot_bytes, uint32_t first_slot, uint32_t sw, uint32_t sh,
                 uint64_t dst_off, uint32_t dw, uint32_t dh, uint32_t dpitch) {
   constexpr int kTileH = 4 * kRpt;
   constexpr int kSrcH = 2 * kTileH + 3;
   constexpr int kRows = 2 * kRpt + 3;  // source rows per thread
-  __shared__ __align__(16) uint8_t tile[kSrcH * kPdSrcW];
+  __shared__ __align__(128) uint8_t tile[kSrcH * kPdSrcW];
+  __shared__ __align__(8) uint64_t bar;
   uint8_t* slot = pyr + (uint64_t)(first_slot + blockIdx.z) * slot_bytes;
-  const uint8_t* src = slot + src_off;
   const int x0t = blockIdx.x * kPdTileW, y0t = blockIdx.y * kTileH;
   const int sx0 = 2 * x0t - 16, sy0 = 2 * y0t - 2;  // source coords of tile[0][0] (16-byte aligned)
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-
-  // ---- stage the source region (reflect at load): warp = row, lane = 16-byte chunk;
-  // only what this tile's outputs read: source cols <= 2*xe, rows <= 2*ye
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                 "r"((uint32_t)(kSrcH * kPdSrcW)) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"((uint32_t)__cvta_generic_to_shared(tile)), "l"(&src_map), "r"(sx0), "r"(sy0),
+        "r"((int)(first_slot + blockIdx.z)), "r"(bar_addr) : "memory");
+  }
+  __syncthreads();  // barrier initialised before anybody polls it
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar_addr), "r"(0u) : "memory");
+    }
+  }
+  // ---- border tiles: BORDER_REFLECT_101 rebuilt in shared memory ----------------------
   {
     const int xe = min(x0t + kPdTileW, (int)dw), ye = min(y0t + kTileH, (int)dh);
-    const int n_rows = 2 * (ye - y0t) + 3;
-    const int cx = sx0 + tx * 16;
-    const int need_lo = 2 * x0t - 2, need_hi = 2 * xe;  // source columns the outputs read
-    // chunks completely inside the image: global -> shared with cp.async (no register
-    // staging, every row's copy in flight at once, no divergence)
-    const bool lane_fast = tx < kPdChunks && cx <= need_hi && cx + 15 >= need_lo && cx >= 0 &&
-                           cx + 16 <= (int)sw;
-    for (int row = ty; row < n_rows; row += 4) {
-      const uint8_t* srow = src + (uint64_t)reflect101_near(sy0 + row, (int)sh) * spitch;
-      if (lane_fast) {
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + row * kPdSrcW + tx * 16);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srow + cx) : "memory");
+    const int n_rows = 2 * (ye - y0t) + 3;                 // source rows sy0 .. sy0+n_rows-1 are read
+    const int need_lo = 2 * x0t - 2, need_hi = 2 * xe;     // source columns the outputs read
+    const bool row_border = sy0 < 0 || sy0 + n_rows > (int)sh;
+    const bool col_border = need_lo < 0 || need_hi >= (int)sw;
+    if (row_border) {  // CTA-uniform
+      for (int i = threadIdx.x; i < n_rows * (kPdSrcW / 16); i += 128) {
+        const int row = i / (kPdSrcW / 16), ch = i - row * (kPdSrcW / 16);
+        const int sy = sy0 + row;
+        if (sy < 0 || sy >= (int)sh) {
+          const int from = reflect101_near(sy, (int)sh) - sy0;  // an in-image row of this tile
+          *reinterpret_cast<uint4*>(tile + row * kPdSrcW + ch * 16) =
+              *reinterpret_cast<const uint4*>(tile + from * kPdSrcW + ch * 16);
+        }
       }
+      __syncthreads();
     }
-    // border columns (left of 0, or from the last whole 16-byte chunk on): thread = row,
-    // a handful of bytes each, through the reflection
-    const int left_hi = min(-1, need_hi);               // columns need_lo .. left_hi
-    const int right_lo = max((int)sw & ~15, need_lo);   // columns right_lo .. need_hi
-    if (need_lo < 0 || need_hi >= ((int)sw & ~15)) {
+    if (col_border) {  // CTA-uniform
       for (int row = threadIdx.x; row < n_rows; row += 128) {
-        const uint8_t* srow = src + (uint64_t)reflect101_near(sy0 + row, (int)sh) * spitch;
-        uint8_t* trow = tile + row * kPdSrcW - sx0;
-        for (int k = need_lo; k <= left_hi; ++k) trow[k] = srow[reflect101_near(k, (int)sw)];
-        for (int k = right_lo; k <= need_hi; ++k) trow[k] = srow[reflect101_near(k, (int)sw)];
+        uint8_t* trow = tile + row * kPdSrcW - sx0;  // trow[k] = source column k
+        for (int k = need_lo; k < 0; ++k) trow[k] = trow[reflect101_near(k, (int)sw)];
+        for (int k = max((int)sw, need_lo); k <= need_hi; ++k) trow[k] = trow[reflect101_near(k, (int)sw)];
       }
+      __syncthreads();
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
   }
-  __syncthreads();
 
   // ---- 4 columns x kRpt rows per thread ------------------------------------------
   const int ox = x0t + 4 * tx, oy = y0t + kRpt * ty;
-  if (ox >= (int)dw || oy >= (int)dh) return;
+  if (tx >= kPdTileW / 4 || ox >= (int)dw || oy >= (int)dh) return;
   // source columns 2*ox-2 .. 2*ox+8 live at tile columns 8*tx+14 .. 8*tx+24
   const uint8_t* tcol = tile + (2 * kRpt * ty) * kPdSrcW + 8 * tx + 8;
   // vertical accumulators, two 16-bit columns per register: a [1 4 6 4 1]^2 sum is at
@@ -276,6 +297,11 @@ pyr_down_small_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t f
   slot[dst_off + (uint64_t)oy * dpitch + ox] = (uint8_t)((acc + 128) >> 8);
 }
 
+typedef CUresult (*PyrEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                     CUtensorMapFloatOOBfill);
+
 cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
                             uint32_t src_level, uint32_t first_slot,
                             uint32_t n_frames, cudaStream_t st) {
@@ -295,11 +321,29 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
   const bool big = (uint64_t)dw * dh * n_frames >= thr;
   const int rpt = big ? (env_rpt ? atoi(env_rpt) : 8) : 2;
   const uint32_t tile_h = 4u * (uint32_t)rpt;
+  // source level as a 3-D tensor (x, y, slot); box = the tile's source region
+  static PyrEncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return cudaErrorNotSupported;
+    encode = reinterpret_cast<PyrEncodeTiledFn>(fp);
+  }
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {lay.w[l], lay.h[l], (cuuint64_t)first_slot + n_frames};
+  const cuuint64_t strides[2] = {lay.pitch[l], lay.slot_bytes};
+  const cuuint32_t box[3] = {(cuuint32_t)kPdSrcW, 2 * tile_h + 3, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + lay.off[l], dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorNotSupported;
   dim3 grid((dw + kPdTileW - 1) / kPdTileW, (dh + tile_h - 1) / tile_h, n_frames);
-#define SVC_PYR_LAUNCH(RPT)                                                                          \
-  pyr_down_kernel<RPT><<<grid, block, 0, st>>>(d_pyr, lay.slot_bytes, first_slot, lay.off[l], lay.w[l], \
-                                               lay.h[l], lay.pitch[l], lay.off[l + 1], dw, dh,       \
-                                               lay.pitch[l + 1])
+#define SVC_PYR_LAUNCH(RPT)                                                                        \
+  pyr_down_kernel<RPT><<<grid, block, 0, st>>>(map, d_pyr, lay.slot_bytes, first_slot, lay.w[l],   \
+                                               lay.h[l], lay.off[l + 1], dw, dh, lay.pitch[l + 1])
   if (rpt == 8) SVC_PYR_LAUNCH(8);
   else if (rpt == 4) SVC_PYR_LAUNCH(4);
   else SVC_PYR_LAUNCH(2);
