@@ -220,6 +220,10 @@ def run_ours(a):
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    if not os.path.exists(svc.lib_path()) and rank == 0:
+        import subprocess  # built artefacts are git-ignored: a fresh checkout builds first
+        subprocess.run(["make", "-C", os.path.join(ROOT, "scalable-video-codec_b200"), "-j4"], check=True,
+                       stdout=subprocess.DEVNULL)
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa_node(local)  # before any pinned allocation (first-touch placement)
     if world > 1:
