@@ -603,7 +603,7 @@ int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, flo
   }
   if (n_enc && d_stream && dct_needs_scratch(dp) && !s->d_scratch) {
     // e.g. a caller-supplied frame pointer that is not 8-byte aligned
-    s->scratch_frames = std::min<uint32_t>(s->info.max_batch, 4);
+    s->scratch_frames = std::min<uint32_t>(s->info.max_batch, 16);
     CU(cudaMalloc(&s->d_scratch, (size_t)s->scratch_frames * 6 * dp.pw * dp.ph * sizeof(float)));
     dp.scratch_planes = s->d_scratch;
     dp.scratch_frames = s->scratch_frames;
@@ -800,7 +800,7 @@ int svc_session_create(const svc_session_config* cfg, svc_session** out) {
   e = cudaStreamSynchronize(s->stream);  // the memsets, before the motion stream may touch the arrays
   if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamSynchronize"));
   if (needs_scratch(s)) {
-    s->scratch_frames = std::min<uint32_t>(s->info.max_batch, 4);
+    s->scratch_frames = std::min<uint32_t>(s->info.max_batch, 16);
     e = cudaMalloc(&s->d_scratch, (size_t)s->scratch_frames * 6 * pw * ph * sizeof(float));
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(scratch)"));
   }
