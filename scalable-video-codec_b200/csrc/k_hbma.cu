@@ -572,19 +572,19 @@ hbma_window_kernel(const __grid_constant__ HbmaWindowMaps maps, const __grid_con
 // ---------------------------------------------------------------------------
 constexpr int kWinWarps = 8;
 
-template <int B>
+template <int B, int NDY>
 __device__ __forceinline__ void window_level_warp(const uint8_t* sW, const int PW, const uint8_t* sA,
                                                   uint16_t* sS, const bool top, const int ncx,
                                                   const int ncy, const int sx_base, const int a_off,
                                                   uint32_t& best_key, bool& any_viol) {
-  constexpr int NDY = 8;
   const int lane = threadIdx.x & 31;
   const int nch = (ncy + NDY - 1) / NDY;
+  const int csz = (ncy + nch - 1) / nch;  // balanced chunks of candidate rows, csz <= NDY
   const int n_items = ncx * nch;
   uint32_t key = 0xffffffffu;
   for (int item = lane; item < n_items; item += 32) {
     const int c = item / ncx, dx = item - c * ncx;
-    const int dy0 = c * NDY, ndy = min(NDY, ncy - dy0);
+    const int dy0 = c * csz, ndy = min(csz, ncy - dy0);
     uint32_t acc[NDY];
 #pragma unroll
     for (int i = 0; i < NDY; ++i) acc[i] = 0;
@@ -612,6 +612,7 @@ __device__ __forceinline__ void window_level_warp(const uint8_t* sW, const int P
   any_viol = __any_sync(0xffffffffu, viol);
 }
 
+template <int NDY16>  // candidate rows per work item at the 16x16 level (chosen from r on the host)
 __global__ void __launch_bounds__(kWinWarps * 32)
 hbma_window_warp_kernel(const __grid_constant__ HbmaWindowMaps maps, const __grid_constant__ HbmaParams p,
                         const __grid_constant__ WinGeom g) {
@@ -681,11 +682,11 @@ hbma_window_warp_kernel(const __grid_constant__ HbmaWindowMaps maps, const __gri
     bool any_viol;
     const int PW = (int)g.box_w[l], sxb = x0 - wx, aoff = ax & 15;
     switch (B) {
-      case 16: window_level_warp<16>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
-      case 8:  window_level_warp<8>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
-      case 4:  window_level_warp<4>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
-      case 2:  window_level_warp<2>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
-      default: window_level_warp<1>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      case 16: window_level_warp<16, NDY16>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      case 8:  window_level_warp<8, NDY16>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      case 4:  window_level_warp<4, 8>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      case 2:  window_level_warp<2, 8>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
+      default: window_level_warp<1, 8>(sW, PW, sA, sS, top, ncx, ncy, sxb, aoff, best, any_viol); break;
     }
     const float m = (float)(best >> 16) * (1.0f / (float)(B * B));
     const int idx = top ? (int)(0xffffu - (best & 0xffffu)) : (int)(best & 0xffffu);
@@ -808,10 +809,27 @@ static bool try_launch_window(const HbmaParams& p, cudaStream_t st, cudaError_t*
   if (g.smem_bytes <= 7 * 1024 && !no_warp) {
     // small windows: one warp per motion block, 8 blocks per CTA
     const uint32_t ctas = (uint32_t)((n_ctas + kWinWarps - 1) / kWinWarps);
-    *err = cudaFuncSetAttribute(hbma_window_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(g.smem_bytes * kWinWarps));
-    if (*err != cudaSuccess) return true;
-    hbma_window_warp_kernel<<<ctas, kWinWarps * 32, g.smem_bytes * kWinWarps, st>>>(maps, p, g);
+    // rows of candidates per work item: the divisor-like choice that wastes the fewest SAD
+    // slots for a (2r+1)-row window (17 rows -> 3 x 6, 33 rows -> 5 x 7, otherwise 8)
+    const uint32_t rows = 2 * r + 1;
+    uint32_t best_ndy = 8, best_cost = 0xffffffffu;
+    for (uint32_t ndy = 6; ndy <= 8; ++ndy) {
+      const uint32_t nch = (rows + ndy - 1) / ndy;
+      const uint32_t rounds = (rows * nch + 31) / 32;          // items per block / 32 lanes
+      const uint32_t cost = rounds * ((15 + ndy) * 9 + 64 * ndy);
+      if (cost < best_cost) { best_cost = cost; best_ndy = ndy; }
+    }
+#define SVC_WARP_WINDOW(NDY)                                                                          \
+  {                                                                                                   \
+    *err = cudaFuncSetAttribute(hbma_window_warp_kernel<NDY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)(g.smem_bytes * kWinWarps));                                      \
+    if (*err != cudaSuccess) return true;                                                             \
+    hbma_window_warp_kernel<NDY><<<ctas, kWinWarps * 32, g.smem_bytes * kWinWarps, st>>>(maps, p, g); \
+  }
+    if (best_ndy == 6) SVC_WARP_WINDOW(6)
+    else if (best_ndy == 7) SVC_WARP_WINDOW(7)
+    else SVC_WARP_WINDOW(8)
+#undef SVC_WARP_WINDOW
     *err = cudaGetLastError();
     return true;
   }
