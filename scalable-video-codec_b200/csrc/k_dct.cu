@@ -18,6 +18,7 @@
 // reference serializer index arithmetic exactly (including its use of the
 // unpadded width as row stride, libs/encoder.cpp:257-262).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -442,8 +443,12 @@ cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* nl) {
       const uint64_t units = (uint64_t)((nbx * nby_total + 31) / 32) * p.n_frames;
       if (units > 0x7fffffffull) return cudaErrorInvalidValue;
       YOut yo{p.y_l0, p.y_slot_bytes, p.y_first_slot, p.y_pitch};
-      if (with_y) dct8x8_stream_kernel<true><<<(uint32_t)units, 96, 0, st>>>(p, nbx, nby, nby_total, yo);
-      else dct8x8_stream_kernel<false><<<(uint32_t)units, 96, 0, st>>>(p, nbx, nby, nby_total, yo);
+      // occupancy knob (experiment hook): extra dynamic shared memory per CTA leaves room on the
+      // SM for the motion-stream kernels that run concurrently
+      static const char* env_pad = getenv("SVC_DCT_SMEM_PAD");
+      const size_t pad = env_pad ? (size_t)atoi(env_pad) : 0;
+      if (with_y) dct8x8_stream_kernel<true><<<(uint32_t)units, 96, pad, st>>>(p, nbx, nby, nby_total, yo);
+      else dct8x8_stream_kernel<false><<<(uint32_t)units, 96, pad, st>>>(p, nbx, nby, nby_total, yo);
       if (nl) *nl += 1;
       e = cudaGetLastError();
       if (e != cudaSuccess) return e;

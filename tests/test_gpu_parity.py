@@ -133,6 +133,20 @@ def test_hbma_flat_frames_tie_break(gpu, oracle):
         assert not mv.any()
 
 
+@pytest.mark.parametrize("R,L", [(8, 4), (64, 4), (20, 1), (24, 2)])
+def test_hbma_saturated_sad_ties(gpu, oracle, R, L):
+    """Tracked all 0, anchor all 255: every candidate has the maximum SAD (MAD 255) -- the widest
+    packed keys, ties everywhere -- on the tiled, warp-window and block-window kernels."""
+    w, h = 176, 112
+    z = [np.zeros((h >> l, w >> l), np.uint8) for l in range(L)]
+    f = [np.full((h >> l, w >> l), 255, np.uint8) for l in range(L)]
+    for t, a in ((z, f), (f, z)):
+        mv, mad = gpu.EstimateMotionHierarchical(t, a, L, w, h, R, 16, 16)
+        emv, emad = oracle.hbma(t, a, R)
+        assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+        assert not mv.any() and (mad == 255.0).all()
+
+
 def test_ebma_zero_range(gpu, oracle):
     rng = np.random.default_rng(3)
     t = rng.integers(0, 256, size=(32, 48)).astype(np.uint8)
