@@ -22,17 +22,9 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "hbma_dev.cuh"
 
 namespace svc {
-
-// acc + sum |a.b[i] - b.b[i]| in ONE instruction (VABSDIFF4.U8.ACC with a live accumulator);
-// the __vsadu4() + add form compiles to VABSDIFF4 ..., RZ plus an IADD3 tree, i.e. 1.5x
-// the integer-ALU work.
-__device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t acc) {
-  uint32_t d;
-  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
-  return d;
-}
 
 // ---------------------------------------------------------------------------
 // Generic kernel: one warp per MV block, lanes stride over the candidates of
@@ -708,37 +700,7 @@ hbma_window_warp_kernel(const __grid_constant__ HbmaWindowMaps maps, const __gri
   }
 }
 
-// ---- host side: tensor maps + dispatch -----------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_tiled() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-static bool encode_box(CUtensorMap* m, const uint8_t* base, uint32_t w, uint32_t h, uint32_t pitch,
-                       uint64_t slot_bytes, uint32_t n_slots, uint32_t box_w, uint32_t box_h) {
-  EncodeTiledFn fn = get_encode_tiled();
-  if (!fn) return false;
-  const cuuint64_t dims[3] = {w, h, n_slots};
-  const cuuint64_t strides[2] = {pitch, slot_bytes};
-  const cuuint32_t box[3] = {box_w, box_h, 1};
-  const cuuint32_t es[3] = {1, 1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
+// ---- host side: dispatch (tensor-map encoding lives in hbma_dev.cuh) ----------------
 template <int L, int R>
 static cudaError_t launch_tile(const HbmaParams& p, cudaStream_t st) {
   using Gm = TileGeom<L, R>;
@@ -848,7 +810,7 @@ cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches) {
   static const bool env_generic = getenv("SVC_HBMA_FORCE_GENERIC") != nullptr;  // test hook
   if (!p.force_generic && !env_generic) {
     cudaError_t e = cudaSuccess;
-    if (try_launch_tile(p, st, &e) || try_launch_window(p, st, &e)) {
+    if (try_launch_tile(p, st, &e) || try_launch_pool(p, st, &e) || try_launch_window(p, st, &e)) {
       if (n_launches) *n_launches += 1;
       return e;
     }

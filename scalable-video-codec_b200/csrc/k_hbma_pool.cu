@@ -1,0 +1,471 @@
+// k_hbma_pool.cu -- K2, large search ranges (16x16 blocks, top-level range r = 5..64): the
+// SAD-bound regime of the range / level sweep (BASELINE config 3).
+//
+// Same arithmetic and scan-order rules as k_hbma.cu (reference libs/motion.cpp:268-465,
+// 691-749); this file only changes how the work is laid out on the SM, to keep the
+// integer-ALU pipe (the binding unit: VABSDIFF4 issues on it at 64 lanes/clk/SM) doing SADs
+// and nothing else:
+//   * per level, each motion block's clamped search window ((B+2r)^2 bytes, position data
+//     dependent on the coarser level's vector) and its anchor block arrive by two TMA tensor
+//     loads; the CTA then writes three more copies of the window, shifted left by 1, 2 and
+//     3 bytes.  A candidate column at byte offset sx reads copy (sx & 3) at word sx >> 2:
+//     every tracked word is a plain aligned LDS with an immediate offset -- no funnel
+//     shifts and no address arithmetic in the SAD loop (the previous kernel spent 1 VIADD +
+//     4 SHF per 32 VABSDIFF4 on them, all on the same pipe).  The copies sit 32 bytes
+//     (mod 128) apart so that the 4 phases x 8 words a warp reads hit 32 different banks;
+//   * a CTA walks NB motion blocks down the pyramid in lock step and pools their work items
+//     (candidate column x chunk of candidate rows) over all its lanes, so windows with an
+//     awkward number of columns (17, 33, 65, 129) still fill whole warps;
+//   * the rows-per-item count NDY is chosen per range class so that 2r+1 candidate rows
+//     split into full chunks (17 = 1x17, 33 = 3x11, 65 = 5x13, 129 = 10x13 - 1);
+//   * the top level's "every candidate updated the minimum => zero vector" rule
+//     (libs/motion.cpp:333-337) is checked with warp shuffles between neighbouring columns;
+//     only items on a warp or window-row boundary go through (small) shared-memory arrays.
+#include <float.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "hbma_dev.cuh"
+
+namespace svc {
+
+struct PoolMaps {
+  CUtensorMap t[5];  // tracked window box per level: PT x (B + 2r)
+  CUtensorMap a[5];  // anchor block box per level: 16 x B
+};
+
+template <int RC, int NB, int NDY>
+struct PoolGeom {
+  static constexpr int PT = (16 + 2 * RC + 15 + 15) & ~15;  // window pitch: block + range + 16-byte origin slack
+  static constexpr int ROWS = 16 + 2 * RC + NDY;            // + slack rows streamed by a short last chunk
+  static constexpr int CS = ((PT * ROWS + 16 + 127) & ~127) + 32;  // copy stride, = 32 (mod 128)
+  static constexpr int BLK = 4 * CS + 256;                  // 4 copies + anchor block (pitch 16)
+  static constexpr int NCH = (2 * RC + 1 + NDY - 1) / NDY;  // chunks of candidate rows
+  static constexpr int MAXWR = (NB * (2 * RC + 1) * NCH + 31) / 32;  // warp rounds per level
+  static constexpr int EDGE = 2 * (MAXWR + NB * NCH) * NDY * 2;      // bytes of u16 edge arrays
+  static constexpr int SMEM = NB * BLK + EDGE;
+};
+
+struct PoolLv {  // one motion block at the current level
+  int x0, y0, ncx, ncy;  // clamped candidate window (origin, size)
+  int nch, csz;          // chunks of candidate rows, rows per chunk (balanced)
+  int sxb, aoff;         // byte offset of x0 inside the TMA box; of the anchor block in its box
+  uint32_t magic;        // ceil(2^32 / ncx) (0 when ncx == 1)
+  int n_items;           // ncx * nch (0: no block)
+};
+
+// NDY vertically adjacent candidates of one candidate column: streams B+NDY-1 aligned rows
+// of the pre-shifted copy once, anchor block in registers.
+template <int B, int NDY, int PT>
+__device__ __forceinline__ void sad_column_pre(const uint8_t* __restrict__ tcol,
+                                               const uint8_t* __restrict__ ablk,
+                                               uint32_t (&acc)[NDY]) {
+  constexpr int NW = B >= 4 ? B / 4 : 1;
+  constexpr uint32_t MASK = B >= 4 ? 0xffffffffu : (B == 2 ? 0xffffu : 0xffu);
+  uint32_t a[B][NW];
+#pragma unroll
+  for (int k = 0; k < B; ++k) {
+    const uint8_t* q = ablk + k * 16;
+    if constexpr (B == 16) {
+      const uint4 v = *reinterpret_cast<const uint4*>(q);
+      a[k][0] = v.x; a[k][1] = v.y; a[k][2] = v.z; a[k][3] = v.w;
+    } else if constexpr (B == 8) {
+      const uint2 v = *reinterpret_cast<const uint2*>(q);
+      a[k][0] = v.x; a[k][1] = v.y;
+    } else if constexpr (B == 4) {
+      a[k][0] = *reinterpret_cast<const uint32_t*>(q);
+    } else if constexpr (B == 2) {
+      a[k][0] = *reinterpret_cast<const uint16_t*>(q);
+    } else {
+      a[k][0] = *q;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < B + NDY - 1; ++t) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(tcol + t * PT);
+    uint32_t tw[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) tw[k] = B >= 4 ? q[k] : (q[k] & MASK);
+#pragma unroll
+    for (int dyi = 0; dyi < NDY; ++dyi) {
+      const int ar = t - dyi;
+      if (ar >= 0 && ar < B) {
+#pragma unroll
+        for (int k = 0; k < NW; ++k) acc[dyi] = sad4_acc(tw[k], a[ar][k], acc[dyi]);
+      }
+    }
+  }
+}
+
+// item -> (block j, chunk c, column dx)
+template <int NB>
+__device__ __forceinline__ void pool_decode(const int item, const int (&beg)[NB + 1], const PoolLv* sLv,
+                                            int& j, int& c, int& dx, int& dy0, int& ndy) {
+  j = 0;
+  int bj = 0;
+#pragma unroll
+  for (int k = 1; k < NB; ++k) {
+    if (item >= beg[k]) { j = k; bj = beg[k]; }  // beg[] is non-decreasing (no dynamic indexing: registers)
+  }
+  const PoolLv& v = sLv[j];
+  const int local = item - bj;
+  c = v.magic ? (int)__umulhi((uint32_t)local, v.magic) : local;
+  dx = local - c * v.ncx;
+  dy0 = c * v.csz;
+  ndy = min(v.csz, v.ncy - dy0);
+}
+
+template <int B, int RC, int NB, int NDY, int THREADS>
+__device__ __forceinline__ void pool_level(const uint8_t* smem, const PoolLv* sLv, const int (&beg)[NB + 1],
+                                           const bool top, uint32_t* sBest, uint32_t* sViol,
+                                           uint16_t* sTailW, uint16_t* sHeadW, uint16_t* sTailC,
+                                           uint16_t* sHeadC) {
+  using G = PoolGeom<RC, NB, NDY>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int total = beg[NB];
+  for (int base = warp * 32; base < total; base += THREADS) {  // warp-uniform trip count
+    const int item = base + lane;
+    const bool act = item < total;
+    int j, c, dx, dy0, ndy;
+    pool_decode<NB>(act ? item : total - 1, beg, sLv, j, c, dx, dy0, ndy);
+    const int ncx = sLv[j].ncx;
+    uint32_t acc[NDY];
+#pragma unroll
+    for (int i = 0; i < NDY; ++i) acc[i] = 0;
+    if (act) {
+      const int sx = sLv[j].sxb + dx;
+      const uint8_t* blk = smem + j * G::BLK;
+      sad_column_pre<B, NDY, G::PT>(blk + (sx & 3) * G::CS + dy0 * G::PT + (sx & ~3),
+                                    blk + 4 * G::CS + sLv[j].aoff, acc);
+    }
+    // packed (sad << 16 | scan index) minimum.  top: "<=" -> the last minimum wins (index stored
+    // complemented); refinement: "<" -> the first minimum wins.  The pack is an integer
+    // multiply-add (FMA pipe), only the minimum runs on the ALU pipe.
+    uint32_t key = 0xffffffffu;
+    {
+      const uint32_t idx0 = (uint32_t)(dy0 * ncx + dx);  // scan order inside the clamped window
+      const uint32_t k0 = top ? 0xffffu - idx0 : idx0;
+      const uint32_t kstep = top ? (uint32_t)(-ncx) : (uint32_t)ncx;
+      uint32_t k[NDY];
+#pragma unroll
+      for (int i = 0; i < NDY; ++i) k[i] = acc[i] * 65536u + (k0 + (uint32_t)i * kstep);
+      if (__all_sync(0xffffffffu, !act || ndy == NDY)) {  // whole chunks: no per-row predicates
+#pragma unroll
+        for (int i = 0; i < NDY; ++i) key = min(key, k[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NDY; ++i) key = min(key, i < ndy ? k[i] : 0xffffffffu);
+      }
+      if (!act) key = 0xffffffffu;
+    }
+    // top level: has the SAD sequence of block j increased anywhere in scan order?  Skipped once
+    // a violation is known (the common case on textured content after the first few items).
+    if (top && __any_sync(0xffffffffu, act && sViol[j] == 0u)) {
+      // the scan-order predecessor of candidate (dx, dy) is (dx-1, dy): the previous lane
+      bool viol = false;
+#pragma unroll
+      for (int i = 0; i < NDY; ++i) {
+        const uint32_t pv = __shfl_up_sync(0xffffffffu, acc[i], 1);
+        viol |= (i < ndy && acc[i] > pv);
+      }
+      viol &= (lane > 0 && dx > 0);
+      if (act) {
+        const int wr = base >> 5;
+        if (lane == 0 && dx > 0) {
+#pragma unroll
+          for (int i = 0; i < NDY; ++i) sHeadW[wr * NDY + i] = (uint16_t)acc[i];
+        }
+        if (lane == 31) {
+#pragma unroll
+          for (int i = 0; i < NDY; ++i) sTailW[wr * NDY + i] = (uint16_t)acc[i];
+        }
+        if (dx == 0) {
+#pragma unroll
+          for (int i = 0; i < NDY; ++i) sHeadC[(j * G::NCH + c) * NDY + i] = (uint16_t)acc[i];
+        }
+        if (dx == ncx - 1) {
+#pragma unroll
+          for (int i = 0; i < NDY; ++i) sTailC[(j * G::NCH + c) * NDY + i] = (uint16_t)acc[i];
+        }
+        if (viol) sViol[j] = 1u;
+      }
+    }
+    if constexpr (NB == 1) {
+      key = __reduce_min_sync(0xffffffffu, key);
+      if (lane == 0) atomicMin(&sBest[0], key);
+    } else {
+      const int j0 = __shfl_sync(0xffffffffu, j, 0);
+      if (__all_sync(0xffffffffu, !act || j == j0)) {
+        key = __reduce_min_sync(0xffffffffu, key);
+        if (lane == 0) atomicMin(&sBest[j0], key);
+      } else if (act) {
+        atomicMin(&sBest[j], key);
+      }
+    }
+  }
+}
+
+template <int RC, int NB, int NDY, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+hbma_pool_kernel(const __grid_constant__ PoolMaps maps, const __grid_constant__ HbmaParams p) {
+  using G = PoolGeom<RC, NB, NDY>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ PoolLv sLv[NB];
+  __shared__ uint32_t sBest[NB], sViol[NB];
+  uint16_t* sTailW = reinterpret_cast<uint16_t*>(smem + NB * G::BLK);
+  uint16_t* sHeadW = sTailW + G::MAXWR * NDY;
+  uint16_t* sTailC = sHeadW + G::MAXWR * NDY;
+  uint16_t* sHeadC = sTailC + NB * G::NCH * NDY;
+
+  const int tid = threadIdx.x;
+  const uint32_t per_frame = p.mvw * p.mvh;
+  const uint64_t n_blocks = (uint64_t)per_frame * p.n_frames;
+  const int r = (int)p.r, L = (int)p.lay.levels;
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+
+  // thread j < NB owns the state of motion block j of this CTA
+  int mx = 0, my = 0, bx = 0, by = 0;
+  float cur = FLT_MAX;
+  uint32_t f = 0, bi = 0;
+  bool own = false;
+  if (tid < NB) {
+    const uint32_t gb = blockIdx.x * NB + tid;  // < 2^31 (checked on the host)
+    own = gb < (uint32_t)n_blocks;
+    if (own) {
+      f = gb / per_frame;
+      bi = gb - f * per_frame;
+      bx = (int)(bi % p.mvw);
+      by = (int)(bi / p.mvw);
+    }
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_addr), "r"(NB));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t parity = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const bool top = (l == L - 1);
+    const int B = 16 >> l;
+    const int box_h = B + 2 * r;
+    int x0 = 0, y0 = 0, ncx = 1, ax = 0, ay = 0;
+    if (tid < NB) {
+      PoolLv v{};
+      if (own) {
+        const int fw = (int)p.lay.w[l], fh = (int)p.lay.h[l];
+        if (!top) { mx *= 2; my *= 2; }
+        ax = bx * B;
+        ay = by * B;
+        const int cx = ax + mx, cy = ay + my;
+        x0 = max(0, cx - r);
+        y0 = max(0, cy - r);
+        const int x1 = min(fw - B + 1, cx + r + 1), y1 = min(fh - B + 1, cy + r + 1);
+        ncx = x1 - x0;
+        const int ncy = y1 - y0;
+        const int nch = (ncy + NDY - 1) / NDY;
+        v.x0 = x0; v.y0 = y0; v.ncx = ncx; v.ncy = ncy;
+        v.nch = nch;
+        v.csz = (ncy + nch - 1) / nch;
+        v.sxb = x0 & 15;
+        v.aoff = ax & 15;
+        v.magic = ncx > 1 ? 0xffffffffu / (uint32_t)ncx + 1u : 0u;
+        v.n_items = ncx * nch;
+        if (p.counters) {
+          atomicAdd(p.counters, (unsigned long long)(ncx * ncy));
+          atomicAdd(p.counters + 1, (unsigned long long)(ncx * ncy) * B * B);
+        }
+      }
+      sLv[tid] = v;
+      sBest[tid] = 0xffffffffu;
+      sViol[tid] = 0u;
+      if (own) {
+        // order the generic-proxy accesses of the previous level before the async-proxy overwrite
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                     "r"((uint32_t)(G::PT * box_h + 16 * B)) : "memory");
+        uint8_t* blk = smem + tid * G::BLK;
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(blk)), "l"(&maps.t[l]), "r"(x0 & ~15), "r"(y0), "r"((int)f),
+            "r"(bar_addr) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(blk + 4 * G::CS)), "l"(&maps.a[l]), "r"(ax & ~15), "r"(ay),
+            "r"((int)f + 1), "r"(bar_addr) : "memory");
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+      }
+    }
+    {  // windows landed; sLv / sBest / sViol published (arrive = release, wait = acquire)
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar_addr), "r"(parity) : "memory");
+      }
+      parity ^= 1u;
+    }
+    // copies shifted left by 1, 2, 3 bytes (copy s, word i = bytes 4i+s .. 4i+s+3 of the window);
+    // all NB windows as one flat list of 16-byte vectors, 4 independent vectors per thread and trip
+    {
+      const int nvec = (G::PT / 16) * box_h, total = NB * nvec;
+      const uint32_t vmagic = 0xffffffffu / (uint32_t)nvec + 1u;
+      const int lane = tid & 31;
+      for (int vb = tid - lane; vb < total; vb += 4 * THREADS) {  // warp-uniform trip count (shuffles inside)
+        const int v0 = vb + lane;
+        uint4 v[4];
+        uint32_t nx[4];
+        uint8_t* dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int vi = min(v0 + u * THREADS, total - 1);
+          const int j = NB > 1 ? (int)__umulhi((uint32_t)vi, vmagic) : 0;
+          uint8_t* q = smem + j * G::BLK + (vi - j * nvec) * 16;
+          v[u] = *reinterpret_cast<const uint4*>(q);
+          dst[u] = q;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          // first word of the next vector: the next lane holds it (lane 31: from shared memory; a
+          // window's last vector takes a word of the slack rows, whose value is never used)
+          nx[u] = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+          if (lane == 31) nx[u] = *reinterpret_cast<const uint32_t*>(dst[u] + 16);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (v0 + u * THREADS < total) {
+#pragma unroll
+            for (int sft = 1; sft < 4; ++sft) {
+              uint4 o;
+              o.x = __funnelshift_r(v[u].x, v[u].y, 8 * sft);
+              o.y = __funnelshift_r(v[u].y, v[u].z, 8 * sft);
+              o.z = __funnelshift_r(v[u].z, v[u].w, 8 * sft);
+              o.w = __funnelshift_r(v[u].w, nx[u], 8 * sft);
+              *reinterpret_cast<uint4*>(dst[u] + sft * G::CS) = o;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    int beg[NB + 1];
+    beg[0] = 0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) beg[j + 1] = beg[j] + sLv[j].n_items;
+    switch (B) {
+      case 16: pool_level<16, RC, NB, NDY, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
+      case 8:  pool_level<8, RC, NB, NDY, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
+      case 4:  pool_level<4, RC, NB, NDY, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
+      case 2:  pool_level<2, RC, NB, NDY, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
+      default: pool_level<1, RC, NB, NDY, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
+    }
+    __syncthreads();
+    if (top) {
+      // scan-order neighbours that were not in adjacent lanes
+      const int total = beg[NB];
+      const int nwr = (total + 31) >> 5;
+      for (int e = tid; e < (nwr - 1) * NDY; e += THREADS) {  // first lane of a warp round vs. last lane of the previous one
+        const int wr = 1 + e / NDY, i = e - (wr - 1) * NDY;
+        int j, c, dx, dy0, ndy;
+        pool_decode<NB>(wr * 32, beg, sLv, j, c, dx, dy0, ndy);
+        if (dx > 0 && i < ndy && sHeadW[wr * NDY + i] > sTailW[(wr - 1) * NDY + i]) sViol[j] = 1u;
+      }
+      for (int e = tid; e < NB * G::NCH * NDY; e += THREADS) {  // first column vs. last column of the previous row
+        const int jc = e / NDY, i = e - jc * NDY;
+        const int j = jc / G::NCH, c = jc - j * G::NCH;
+        const PoolLv& v = sLv[j];
+        if (v.n_items == 0 || c >= v.nch) continue;
+        if (i >= min(v.csz, v.ncy - c * v.csz)) continue;
+        uint32_t pv;
+        if (i > 0) pv = sTailC[jc * NDY + i - 1];
+        else if (c > 0) pv = sTailC[(jc - 1) * NDY + v.csz - 1];  // only the last chunk can be short
+        else continue;
+        if (sHeadC[jc * NDY + i] > pv) sViol[j] = 1u;
+      }
+      __syncthreads();
+    }
+    if (own) {  // tid < NB
+      const uint32_t best = sBest[tid];
+      const float m = (float)(best >> 16) * (1.0f / (float)(B * B));
+      const int idx = top ? (int)(0xffffu - (best & 0xffffu)) : (int)(best & 0xffffu);
+      const int nmx = x0 + idx % ncx - ax, nmy = y0 + idx / ncx - ay;
+      if (top) {
+        const bool any_viol = sViol[tid] != 0u;
+        cur = m;
+        mx = any_viol ? nmx : 0;
+        my = any_viol ? nmy : 0;
+      } else if (m < cur) {
+        cur = m;
+        mx = nmx;
+        my = nmy;
+      }
+    }
+  }
+  if (own) {
+    const uint64_t o = (uint64_t)f * per_frame + bi;
+    if (p.mv) p.mv[o] = make_float2((float)mx, (float)my);
+    if (p.mad) p.mad[o] = cur;
+  }
+}
+
+template <int RC, int NB, int NDY, int THREADS, int MINB>
+static cudaError_t launch_pool(const HbmaParams& p, cudaStream_t st) {
+  using G = PoolGeom<RC, NB, NDY>;
+  static_assert(G::SMEM <= 227 * 1024, "pool geometry does not fit");
+  static_assert(G::PT <= 256, "TMA box limit");
+  const uint32_t L = p.lay.levels, r = p.r;
+  PoolMaps maps;
+  const uint32_t n_slots = p.n_frames + 1;
+  for (uint32_t l = 0; l < L; ++l) {
+    const uint32_t B = 16u >> l;
+    const uint8_t* base = p.pyr + p.lay.off[l];
+    if (!encode_box(&maps.t[l], base, p.lay.w[l], p.lay.h[l], p.lay.pitch[l], p.lay.slot_bytes, n_slots,
+                    G::PT, B + 2 * r) ||
+        !encode_box(&maps.a[l], base, p.lay.w[l], p.lay.h[l], p.lay.pitch[l], p.lay.slot_bytes, n_slots, 16, B))
+      return cudaErrorNotSupported;
+  }
+  auto kern = hbma_pool_kernel<RC, NB, NDY, THREADS, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+  if (e != cudaSuccess) return e;
+  const uint64_t n_blocks = (uint64_t)p.mvw * p.mvh * p.n_frames;
+  kern<<<(uint32_t)((n_blocks + NB - 1) / NB), THREADS, G::SMEM, st>>>(maps, p);
+  return cudaGetLastError();
+}
+
+bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
+  static const bool off = getenv("SVC_HBMA_NO_POOL") != nullptr;  // experiment hook
+  const uint32_t L = p.lay.levels, r = p.r;
+  if (off || p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > 64) return false;
+  if ((uint64_t)p.mvw * p.mvh * p.n_frames > 0x7fffffffull) return false;
+  // Deep pyramids with a small top-level range are dominated by the per-level fixed costs (TMA
+  // round trip, copy build, barriers) of the small coarse levels: the warp-per-block window
+  // kernel of k_hbma.cu, which has no block-wide barrier, measures a little faster there.
+  const bool force = getenv("SVC_HBMA_FORCE_POOL") != nullptr;  // test / experiment hook (read per launch)
+  if (L >= 3 && r <= 16 && !force) return false;
+  static const char* env_v = getenv("SVC_HBMA_POOL_VARIANT");  // tuning hook
+  const int variant = env_v ? atoi(env_v) : 0;
+  // <range class, blocks per CTA, candidate rows per item, threads, CTAs per SM>: measured best of
+  // several shapes per class on B200 (profiles/r01_sweep_hbma_v5.md)
+  if (r <= 8) {
+    if (variant == 1) *err = launch_pool<8, 8, 9, 128, 3>(p, st);
+    else *err = launch_pool<8, 7, 17, 128, 3>(p, st);
+  } else if (r <= 16) {
+    if (variant == 1) *err = launch_pool<16, 4, 11, 128, 3>(p, st);
+    else *err = launch_pool<16, 3, 11, 128, 4>(p, st);
+  } else if (r <= 32) {
+    if (variant == 1) *err = launch_pool<32, 3, 13, 256, 2>(p, st);
+    else *err = launch_pool<32, 2, 13, 128, 3>(p, st);
+  } else {
+    if (variant == 1) *err = launch_pool<64, 1, 10, 256, 2>(p, st);
+    else *err = launch_pool<64, 1, 13, 256, 2>(p, st);
+  }
+  return true;
+}
+
+}  // namespace svc

@@ -123,6 +123,45 @@ def test_hbma_window_path_vs_oracle(gpu, oracle, L, R, w, h):
     assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
 
 
+@pytest.mark.parametrize("L,R", [(1, 5), (1, 8), (1, 12), (1, 16), (1, 27), (1, 32), (1, 50), (1, 64),
+                                 (2, 16), (2, 34), (2, 64), (2, 128), (3, 32), (3, 64), (3, 128),
+                                 (4, 64), (4, 128), (5, 128)])
+@pytest.mark.parametrize("w,h", [(416, 240), (48, 176)])
+def test_hbma_pooled_window_path_vs_oracle(gpu, oracle, L, R, w, h, monkeypatch):
+    """16x16 blocks, top-level range 5..64: the pooled kernel with pre-shifted window copies
+    (every range class, ranges inside a class, interior blocks with unclamped windows as well as
+    windows clamped on every side, a frame narrower than the window, flat-patch ties)."""
+    monkeypatch.setenv("SVC_HBMA_FORCE_POOL", "1")  # also where the dispatcher prefers the warp kernel
+    pw, ph = gpu.padded_dim(w, 16, L), gpu.padded_dim(h, 16, L)
+    seq = SyntheticSequence(w, h, 2, seed=L * 13 + R)
+    p0, p1 = oracle.y_pyramid(seq.frame(0), pw, ph, L), oracle.y_pyramid(seq.frame(1), pw, ph, L)
+    mv, mad = gpu.EstimateMotionHierarchical(p0, p1, L, pw, ph, R, 16, 16)
+    emv, emad = oracle.hbma(p0, p1, R)
+    assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+
+
+@pytest.mark.parametrize("R,L", [(8, 1), (16, 1), (32, 1), (64, 1), (64, 2)])
+def test_hbma_pooled_window_monotone_sequences(gpu, oracle, R, L):
+    """Top-level zero-vector rule (libs/motion.cpp:333-337) on the pooled kernel: horizontal /
+    vertical ramps and constant frames make the SAD sequence non-increasing over whole windows
+    for some blocks and break it by a single candidate for others."""
+    w, h = 224, 160
+    yy, xx = np.mgrid[0:h, 0:w]
+    bases = [np.clip(xx, 0, 255), np.clip(yy, 0, 255), np.clip(255 - xx - yy // 2, 0, 255),
+             np.full((h, w), 7), np.clip((xx // 16) * 9 + (yy // 16) * 5, 0, 255)]
+    def pyr(img):
+        out = [img.astype(np.uint8)]
+        for _ in range(L - 1):
+            out.append(oracle.pyr_down(out[-1]))
+        return out
+    for i, a in enumerate(bases):
+        for t in (bases[(i + 1) % len(bases)], a):
+            tp, ap = pyr(t), pyr(a)
+            mv, mad = gpu.EstimateMotionHierarchical(tp, ap, L, w, h, R, 16, 16)
+            emv, emad = oracle.hbma(tp, ap, R)
+            assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+
+
 def test_hbma_flat_frames_tie_break(gpu, oracle):
     z = [np.zeros((64 >> l, 96 >> l), np.uint8) for l in range(4)]
     c = [np.full((64 >> l, 96 >> l), 9, np.uint8) for l in range(4)]
