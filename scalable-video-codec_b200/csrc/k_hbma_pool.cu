@@ -162,7 +162,8 @@ __device__ __forceinline__ void pool_level(const uint8_t* smem, const PoolLv* sL
     }
     // top level: has the SAD sequence of block j increased anywhere in scan order?  Skipped once
     // a violation is known (the common case on textured content after the first few items).
-    if (top && __any_sync(0xffffffffu, act && sViol[j] == 0u)) {
+    // (volatile: the flag is raised by other warps while this one loops)
+    if (top && __any_sync(0xffffffffu, act && *reinterpret_cast<volatile uint32_t*>(&sViol[j]) == 0u)) {
       // the scan-order predecessor of candidate (dx, dy) is (dx-1, dy): the previous lane
       bool viol = false;
 #pragma unroll
