@@ -207,3 +207,85 @@ def decode_frame_blocks(records, pw, ph, tbw=8, tbh=8, fg_q=1, bg_q=640, gaze=No
     if rc != 0:
         raise ValueError("orc_decode_frame_blocks: bad block size")
     return out
+
+
+# ---- block-type stages (libs/encoder.cpp:491-624): the checkers are the compiled reference
+# ---- (RANSAC) and python cv2 (morphologyEx, kmeans, connectedComponents) -------------------
+_ref_copies = {}
+
+
+def ref_seeded(seed: int, fresh: bool = True):
+    """A private copy of the compiled reference whose function-static RANSAC engine
+    (libs/motion.cpp:186-187) will be seeded with `seed` on its first call: the engine is
+    seeded once per loaded library image, so every request gets its own image (fresh=False
+    returns the image already loaded for that seed, with its engine state carried on)."""
+    if not fresh and seed in _ref_copies:
+        return _ref_copies[seed]
+    import shutil
+    import tempfile
+    src = os.path.join(_HERE, "_ref", "libref_motion.so")
+    if not os.path.exists(src):
+        return None
+    d = tempfile.mkdtemp(prefix="svc_ref_")
+    p = os.path.join(d, "libref_motion_%d_%d.so" % (seed, len(_ref_copies)))
+    shutil.copy(src, p)
+    L = C.CDLL(p)
+    if not hasattr(L, "ref_ransac"):
+        return None
+    L.ref_set_seed(C.c_uint(seed))
+    _ref_copies[seed] = L
+    _ref_copies[("all", len(_ref_copies))] = L  # keep every image alive
+    return L
+
+
+def ref_ransac(L, mv, subset_sz=1, inlier_thresh=7.5, success_prob=0.99, inlier_ratio=0.5, gm0=(0.0, 0.0)):
+    """EstimateGlobalMotionRansac of the compiled reference image `L` (see ref_seeded)."""
+    mv = np.ascontiguousarray(mv, np.float32).reshape(-1, 2)
+    n = mv.shape[0]
+    buf = np.zeros((n + 1, 2), np.float32)  # the reference may read index n (libs/motion.cpp:208)
+    buf[:n] = mv
+    buf[n] = np.nan
+    rm, ni = C.c_float(), C.c_uint32()
+    gm = np.array(gm0, np.float32)
+    inl = np.zeros(n, np.uint32)
+    L.ref_ransac(buf.ctypes.data_as(_f32p), n, subset_sz, C.c_float(inlier_thresh), C.c_float(success_prob),
+                 C.c_float(inlier_ratio), C.byref(rm), gm.ctypes.data_as(_f32p),
+                 inl.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(ni))
+    return rm.value, gm, inl[:ni.value].copy()
+
+
+def block_types_cv2(mv_field, inliers, kmeans_seed, morph_rect=(3, 3), cluster_count=10, attempts=3,
+                    max_iter=10, eps=1.0, connectivity=4, mv_block=(16, 16)):
+    """libs/encoder.cpp:507-624 with python cv2 standing in for the C++ OpenCV calls, given the
+    RANSAC inliers.  Returns block types (h x w, uint32)."""
+    import cv2
+    mv = np.asarray(mv_field, np.float32)
+    h, w = mv.shape[:2]
+    mask = np.full((h, w), 255, np.uint8)
+    mask.reshape(-1)[np.asarray(inliers, np.int64)] = 0
+    el = cv2.getStructuringElement(cv2.MORPH_RECT, morph_rect)
+    mask = cv2.morphologyEx(mask, cv2.MORPH_CLOSE, el)
+    mask = cv2.morphologyEx(mask, cv2.MORPH_OPEN, el)
+    fg = np.flatnonzero(mask.reshape(-1) == 255)
+    types = np.zeros(h * w, np.uint32)
+    if fg.size == 0:
+        return types.reshape(h, w)
+    k = min(cluster_count, fg.size)
+    feats = np.zeros((fg.size, 1, 4), np.float32)  # BuildMvFeatures quirk: (0, mv.x, x, y)
+    feats[:, 0, 1] = mv.reshape(-1, 2)[fg, 0]
+    feats[:, 0, 2] = (fg % w) * mv_block[0]
+    feats[:, 0, 3] = (fg // w) * mv_block[1]
+    cv2.setRNGSeed(kmeans_seed)
+    _, ids, _ = cv2.kmeans(feats, k, None, (cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, max_iter, eps),
+                           attempts, cv2.KMEANS_PP_CENTERS)
+    ids = ids.reshape(-1)
+    offset = 0
+    for cid in range(k):
+        cm = np.zeros(h * w, np.uint8)
+        cm[fg[ids == cid]] = 255
+        n, lab = cv2.connectedComponents(cm.reshape(h, w), connectivity=connectivity, ltype=cv2.CV_32S)
+        lab = lab.reshape(-1)
+        sel = fg[lab[fg] != 0]
+        types[sel] = lab[sel] + offset
+        offset += n
+    return types.reshape(h, w)

@@ -6,9 +6,47 @@
 // copied into this repository) into oracle/_ref/libref_motion.so by
 // oracle/Makefile.  Used by tests/ to pin the oracle and by
 // `bench.py --impl reference` as the CPU baseline of kind "reference".
+#include <random>
+#include <vector>
+
 #include "motion.hpp"  // -I$(REF)/libs
 
+// EstimateGlobalMotionRansac seeds a function-static std::default_random_engine from
+// std::random_device (libs/motion.cpp:186-187).  To pin that seed WITHOUT touching the reference
+// source, this library defines std::random_device::_M_getval() itself and is linked with
+// -Wl,-Bsymbolic, so the reference's rdev() call binds here.  The engine is seeded on the first
+// call per loaded copy of the library: a test that wants another seed loads another copy.
+static unsigned g_ref_seed = 1;
+unsigned int std::random_device::_M_getval() { return g_ref_seed; }
+
 extern "C" {
+
+void ref_set_seed(unsigned seed) { g_ref_seed = seed; }
+
+// libs/motion.hpp:99-103; inliers: room for n entries; mv_xy must hold n + 1 vectors (the
+// reference samples index n too, libs/motion.cpp:208)
+void ref_ransac(const float* mv_xy, uint n, uint subset_sz, float inlier_thresh, float success_prob,
+                float inlier_ratio, float* rmse, float* gm_xy, uint* inliers, uint* n_inliers) {
+  RansacParams p;
+  p.subset_sz = subset_sz;
+  p.inlier_thresh = inlier_thresh;
+  p.success_prob = success_prob;
+  p.inlier_ratio = inlier_ratio;
+  std::vector<uint> in;
+  Vec2f gm{gm_xy[0], gm_xy[1]};
+  EstimateGlobalMotionRansac(reinterpret_cast<const Vec2f*>(mv_xy), n, p, rmse, &gm, &in);
+  gm_xy[0] = gm.x;
+  gm_xy[1] = gm.y;
+  *n_inliers = (uint)in.size();
+  for (size_t i = 0; i < in.size(); ++i) inliers[i] = in[i];
+}
+
+// libs/motion.hpp:40
+void ref_global_motion_avg(const float* mv_xy, uint n, float* gm_xy) {
+  const Vec2f g = EstimateGlobalMotionAvg(reinterpret_cast<const Vec2f*>(mv_xy), n);
+  gm_xy[0] = g.x;
+  gm_xy[1] = g.y;
+}
 
 // libs/motion.hpp:106-110
 void ref_ebma(const uchar* tracked, const uchar* anchor, uint fw, uint fh,

@@ -6,9 +6,9 @@
 // no C++ OpenCV, so the frame source is raw interleaved 8-bit BGR (file or stdin), e.g.
 //   ffmpeg -i in.mp4 -f rawvideo -pix_fmt bgr24 - | svc_encoder --width W --height H - > out.svc
 // Options keep the reference's names (apps/encoder.cpp:75-104) for the hot-path fields.
-// Block types: every block BLOCK_TYPE_BACKGROUND unless the CPU segmentation stages
-// (RANSAC .. connected components, out of scope here) are supplied through
-// svc::Encoder's callback by an embedding application.
+// Options keep the reference's names for the block-type stages too (RANSAC, morphology,
+// k-means, connected components: host/segment.hpp); --segment 0 leaves every block
+// BLOCK_TYPE_BACKGROUND, --seed makes the labels reproducible.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,6 +25,11 @@ static void usage() {
                "usage: svc_encoder --width W --height H [--frames N] [--mv-search-range R]\n"
                "                   [--pyr-lvl-count L] [--mv-block-w B] [--mv-block-h B]\n"
                "                   [--transform-block-w T] [--transform-block-h T] [--device D]\n"
+               "                   [--ransac-subset-sz N] [--ransac-inlier-thresh T] [--ransac-success-prob P]\n"
+               "                   [--ransac-inlier-ratio W] [--morph-rect-w M] [--morph-rect-h M]\n"
+               "                   [--kmeans-cluster-count K] [--kmeans-attempt-count A] [--kmeans-max-iter-count I]\n"
+               "                   [--kmeans-epsilon E] [--connected-components-connectivity 4|8]\n"
+               "                   [--segment 0|1] [--seed S] [--classify-threads T]\n"
                "                   [--batch K] [--verbose 0|1] <raw-bgr-file | ->\n"
                "       svc_encoder ... --devices 0,1,2,3 --out stream.svc <raw-bgr-file>\n"
                "         (frame-range sharded over several GPUs, one host thread per GPU)\n");
@@ -43,6 +48,10 @@ int main(int argc, char** argv) {
       if (i + 1 >= argc) { usage(); std::exit(EXIT_FAILURE); }
       out = (unsigned)std::strtoul(argv[++i], nullptr, 10);
     };
+    auto fval = [&](float& out) {
+      if (i + 1 >= argc) { usage(); std::exit(EXIT_FAILURE); }
+      out = std::strtof(argv[++i], nullptr);
+    };
     unsigned tmp;
     if (a == "--width") val(width);
     else if (a == "--height") val(height);
@@ -53,6 +62,20 @@ int main(int argc, char** argv) {
     else if (a == "--mv-block-h") val(cfg.mv_block_h);
     else if (a == "--transform-block-w") val(cfg.transform_block_w);
     else if (a == "--transform-block-h") val(cfg.transform_block_h);
+    else if (a == "--ransac-subset-sz") val(cfg.seg.ransac.subset_sz);
+    else if (a == "--ransac-inlier-thresh") fval(cfg.seg.ransac.inlier_thresh);
+    else if (a == "--ransac-success-prob") fval(cfg.seg.ransac.success_prob);
+    else if (a == "--ransac-inlier-ratio") fval(cfg.seg.ransac.inlier_ratio);
+    else if (a == "--morph-rect-w") val(cfg.seg.morph_rect_w);
+    else if (a == "--morph-rect-h") val(cfg.seg.morph_rect_h);
+    else if (a == "--kmeans-cluster-count") val(cfg.seg.kmeans.cluster_count);
+    else if (a == "--kmeans-attempt-count") val(cfg.seg.kmeans.attempt_count);
+    else if (a == "--kmeans-max-iter-count") val(cfg.seg.kmeans.max_iter_count);
+    else if (a == "--kmeans-epsilon") fval(cfg.seg.kmeans.epsilon);
+    else if (a == "--connected-components-connectivity") val(cfg.seg.connected_components_connectivity);
+    else if (a == "--segment") { val(tmp); cfg.segment = tmp != 0; }
+    else if (a == "--seed") { if (i + 1 >= argc) { usage(); return EXIT_FAILURE; } cfg.seed = std::strtoull(argv[++i], nullptr, 10); }
+    else if (a == "--classify-threads") val(cfg.classify_threads);
     else if (a == "--batch") val(cfg.max_batch);
     else if (a == "--device") { val(tmp); cfg.device = (int)tmp; }
     else if (a == "--verbose") { val(tmp); verbose = (int)tmp; }

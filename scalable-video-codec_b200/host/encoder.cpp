@@ -22,6 +22,11 @@ Status Validate(const EncoderConfig& cfg) {
     return {ErrorCode::kInvalidParameter,
             "invalid mv search and pyramid level count: the quotient from dividing the mv search "
             "range by the pyramid level reduction factor must be > 0"};
+  if (cfg.segment) {  // Validate(ransac), Validate(kmeans), connectivity: libs/encoder.cpp:86-101
+    SegmentConfig sc = cfg.seg;
+    const char* m = ValidateSegmentConfig(sc);
+    if (*m) return {ErrorCode::kInvalidParameter, m};
+  }
   if (cfg.transform_block_w < 1)
     return {ErrorCode::kInvalidParameter, "invalid transform block width: must be > 0"};
   if (cfg.transform_block_h < 1)
@@ -80,6 +85,12 @@ Encoder::Encoder(const EncoderConfig& cfg, const VideoProperties& vidprops,
   h_mv_ = static_cast<float*>(svc_host_alloc(B * mvn * 2 * sizeof(float)));
   h_mad_ = static_cast<float*>(svc_host_alloc(B * mvn * sizeof(float)));
   if (!h_in_ || !h_stream_ || !h_mv_ || !h_mad_) throw Error(SVC_ERR_CUDA, "pinned allocation failed");
+  if (!classify_ && cfg_.segment) {
+    SegmentConfig sc = cfg_.seg;
+    sc.mv_block_w = cfg_.mv_block_w;
+    sc.mv_block_h = cfg_.mv_block_h;
+    stage_.reset(new BlockTypeStage(sc, mv_field_w_, mv_field_h_, cfg_.seed, cfg_.classify_threads));
+  }
 }
 
 Encoder::~Encoder() {
@@ -101,6 +112,7 @@ void Encoder::operator()() {
   }
   const size_t mvn = (size_t)mv_field_w_ * mv_field_h_;
   std::vector<uint> block_types(mvn);
+  std::vector<uint> batch_types;
   svc_session_info info{};
   check(svc_session_info_get(session_, &info));
   Frame frame;
@@ -115,9 +127,17 @@ void Encoder::operator()() {
     } while (n < info.max_batch && in_queue_.TryPop(frame));
     uint n_enc = 0;
     check(svc_session_encode(session_, h_in_, n, h_mv_, h_mad_, h_stream_, nullptr, &n_enc));
+    if (stage_ && n_enc) {  // libs/encoder.cpp:491-624 for the whole batch, on worker threads
+      batch_types.resize((size_t)n_enc * mvn);
+      stage_->Run(reinterpret_cast<const Vec2f*>(h_mv_), n_enc, frames_encoded_, batch_types.data());
+    }
     for (uint i = 0; i < n_enc; ++i) {
       uchar* rec = h_stream_ + (size_t)i * frame_stream_bytes_;
-      if (classify_) {
+      if (stage_) {
+        check(svc_patch_block_types(rec, vidprops_.frame_w, vidprops_.frame_h, cfg_.transform_block_w,
+                                    cfg_.transform_block_h, 3, cfg_.mv_block_w, cfg_.mv_block_h,
+                                    mv_field_w_, batch_types.data() + (size_t)i * mvn));
+      } else if (classify_) {
         std::fill(block_types.begin(), block_types.end(), 0u);  // BLOCK_TYPE_BACKGROUND, libs/encoder.cpp:549-551
         classify_(reinterpret_cast<const Vec2f*>(h_mv_ + (size_t)i * mvn * 2), h_mad_ + (size_t)i * mvn,
                   mv_field_w_, mv_field_h_, block_types.data());

@@ -11,10 +11,11 @@
 // differs, because the image has no C++ OpenCV: frames are raw interleaved
 // 8-bit BGR buffers instead of cv::Mat3b, and the CPU stages that turn a
 // motion field into block types (RANSAC .. connected components,
-// libs/encoder.cpp:491-624, out of scope for the GPU path) are supplied by the
-// application as a callback; without one every block is BLOCK_TYPE_BACKGROUND.
-// The callback's labels are patched into the records the GPU already wrote
-// (svc_patch_block_types), so the consumers downstream see the reference layout.
+// libs/encoder.cpp:491-624) are the restatements of host/segment.hpp, run on
+// worker threads over each GPU batch (EncoderConfig::segment; an application
+// can substitute its own callback).  The labels are patched into the records
+// the GPU already wrote (svc_patch_block_types), so the consumers downstream
+// see the reference layout.
 #ifndef SVC_B200_HOST_ENCODER_HPP
 #define SVC_B200_HOST_ENCODER_HPP
 
@@ -26,7 +27,10 @@
 #include <string>
 #include <vector>
 
+#include <memory>
+
 #include "motion.hpp"
+#include "segment.hpp"
 
 struct svc_session;
 
@@ -49,6 +53,13 @@ struct EncoderConfig {
   uint transform_block_h = 8;
   int device = 0;
   uint max_batch = 32;  // frames per kernel launch
+  // Block-type stages (libs/encoder.cpp:491-624: RANSAC, morphology, k-means, connected components),
+  // run on host worker threads over the motion fields of each GPU batch; fields as in the
+  // reference's EncoderConfig (ransac, morph_rect_w/h, kmeans, connected_components_connectivity).
+  bool segment = true;
+  SegmentConfig seg;
+  uint64_t seed = 0;          // 0: from std::random_device like the reference; else reproducible labels
+  uint classify_threads = 0;  // 0: min(8, hardware threads)
 };
 
 struct VideoProperties {  // libs/encoder.hpp:46-50
@@ -134,6 +145,7 @@ class Encoder {
   BoundedQueue<Frame>& in_queue_;
   BoundedQueue<Bytes>& out_queue_;
   BlockTypeFn classify_;
+  std::unique_ptr<BlockTypeStage> stage_;
   svc_session* session_ = nullptr;
   uint padded_frame_w_ = 0, padded_frame_h_ = 0, mv_field_w_ = 0, mv_field_h_ = 0;
   uint64_t frame_stream_bytes_ = 0, frame_in_bytes_ = 0;

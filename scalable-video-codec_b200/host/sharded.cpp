@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <exception>
+#include <memory>
 #include <thread>
 
 #include "../../include/svc_b200.h"
@@ -70,7 +71,14 @@ void run_shard(const EncoderConfig& cfg, const VideoProperties& vp, const std::s
   check(svc_session_info_get(s, &info));
   const size_t B = info.max_batch, mvn = (size_t)info.mv_field_w * info.mv_field_h;
   Pinned h_in(B * info.frame_in_bytes), h_st(B * info.frame_stream_bytes), h_mv(B * mvn * 8), h_mad(B * mvn * 4);
-  std::vector<uint> bt(mvn);
+  std::vector<uint> bt(mvn), batch_types;
+  std::unique_ptr<BlockTypeStage> stage;
+  if (!classify && cfg.segment) {
+    SegmentConfig sc = cfg.seg;
+    sc.mv_block_w = cfg.mv_block_w;
+    sc.mv_block_h = cfg.mv_block_h;
+    stage.reset(new BlockTypeStage(sc, info.mv_field_w, info.mv_field_h, cfg.seed, cfg.classify_threads));
+  }
   FILE* in = std::fopen(in_path.c_str(), "rb");
   if (!in) throw Error(SVC_ERR_INVALID_ARG, "Failed to open " + in_path);
   struct FGuard { FILE* f; ~FGuard() { std::fclose(f); } } fguard{in};
@@ -83,9 +91,17 @@ void run_shard(const EncoderConfig& cfg, const VideoProperties& vp, const std::s
     uint n_enc = 0;
     check(svc_session_encode(s, static_cast<const uint8_t*>(h_in.p), n, static_cast<float*>(h_mv.p),
                              static_cast<float*>(h_mad.p), static_cast<uint8_t*>(h_st.p), nullptr, &n_enc));
+    if (stage && n_enc) {  // per-frame generators depend on the global frame index only
+      batch_types.resize((size_t)n_enc * mvn);
+      stage->Run(reinterpret_cast<const Vec2f*>(h_mv.p), n_enc, next_enc - 1, batch_types.data());
+    }
     for (uint i = 0; i < n_enc; ++i) {
       uchar* rec = static_cast<uchar*>(h_st.p) + (size_t)i * info.frame_stream_bytes;
-      if (classify) {
+      if (stage) {
+        check(svc_patch_block_types(rec, vp.frame_w, vp.frame_h, cfg.transform_block_w, cfg.transform_block_h, 3,
+                                    cfg.mv_block_w, cfg.mv_block_h, info.mv_field_w,
+                                    batch_types.data() + (size_t)i * mvn));
+      } else if (classify) {
         std::fill(bt.begin(), bt.end(), 0u);
         classify(reinterpret_cast<const Vec2f*>(static_cast<float*>(h_mv.p) + (size_t)i * mvn * 2),
                  static_cast<float*>(h_mad.p) + (size_t)i * mvn, info.mv_field_w, info.mv_field_h, bt.data());

@@ -58,8 +58,8 @@ def test_encoder_app_stream_matches_oracle(gpu, oracle, tmp_path):
     frames = SyntheticSequence(w, h, n, seed=31).frames()
     raw = tmp_path / "in.bgr"
     raw.write_bytes(frames.tobytes())
-    r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "4", "--verbose", "0", str(raw)],
-                       capture_output=True, timeout=300)
+    r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "4", "--verbose", "0",
+                        "--segment", "0", str(raw)], capture_output=True, timeout=300)
     assert r.returncode == 0, r.stderr
     out = np.frombuffer(r.stdout, np.uint8)
     pw, ph = oracle.padded_dim(w, 16, 4), oracle.padded_dim(h, 16, 4)
@@ -89,11 +89,55 @@ def test_encoder_app_sharded_output_is_identical_to_single_device(gpu, tmp_path)
     for devs in ("0", "0,0", "0,0,0"):
         out = tmp_path / ("out_%d.svc" % len(devs))
         r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "4", "--verbose", "0",
-                            "--devices", devs, "--out", str(out), str(raw)], capture_output=True, timeout=300)
+                            "--seed", "7", "--devices", devs, "--out", str(out), str(raw)],
+                           capture_output=True, timeout=300)
         assert r.returncode == 0, r.stderr
         outs.append(out.read_bytes())
-    r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "4", "--verbose", "0", str(raw)],
-                       capture_output=True, timeout=300)
+    r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "3", "--verbose", "0",
+                        "--seed", "7", "--classify-threads", "3", str(raw)], capture_output=True, timeout=300)
     assert r.returncode == 0, r.stderr
+    assert np.frombuffer(outs[0], np.uint8)[32:].view(np.uint32).reshape(-1, 193)[:, 0].any()  # real block types
     assert len(outs[0]) == 32 + (n - 1) * gpu.serialized_frame_bytes(w, h)
     assert outs[0] == outs[1] == outs[2] == r.stdout
+
+
+@pytest.mark.gpu
+def test_encoder_app_block_types_follow_the_reference_chain(gpu, oracle, tmp_path):
+    """The application's stream carries the block types of libs/encoder.cpp:491-624 computed from the
+    GPU motion field: RANSAC (compiled reference), morphology / k-means / connected components
+    (python cv2) on the ORACLE's motion field, with the per-frame generator states of --seed."""
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")  # noqa: F841
+    from svc_b200 import segment as seg
+    from svc_b200.synth import SyntheticSequence
+    _build_app()
+    w, h, n, seed = 640, 368, 5, 5
+    frames = SyntheticSequence(w, h, n, seed=77).frames()
+    raw = tmp_path / "in.bgr"
+    raw.write_bytes(frames.tobytes())
+    r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "3", "--verbose", "0",
+                        "--seed", str(seed), "--kmeans-cluster-count", "4", "--ransac-inlier-thresh", "2.5", str(raw)],
+                       capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = np.frombuffer(r.stdout, np.uint8)
+    pw, ph = oracle.padded_dim(w, 16, 4), oracle.padded_dim(h, 16, 4)
+    mw, mh = pw // 16, ph // 16
+    fb = oracle.serialized_frame_bytes(w, h)
+    assert out.size == 32 + (n - 1) * fb
+    pyr = [oracle.y_pyramid(frames[i], pw, ph, 4) for i in range(n)]
+    any_fg = False
+    for t in range(1, n):
+        mv, _ = oracle.hbma(pyr[t - 1], pyr[t], 8)
+        rs, ks = seg.frame_generators(seed, t - 1)
+        L = oracle.ref_seeded(rs)
+        if L is None:
+            pytest.skip("oracle/_ref not built")
+        _, _, inl = oracle.ref_ransac(L, mv, 1, 2.5, 0.99, 0.5)
+        exp = oracle.block_types_cv2(mv, inl, ks, cluster_count=4).reshape(-1)
+        assert np.array_equal(seg.block_types(mv, seg.SegmentConfig(kmeans_cluster_count=4, ransac_inlier_thresh=2.5),
+                                              rs, ks)[0].reshape(-1), exp)
+        got = out[32 + (t - 1) * fb: 32 + t * fb].view(np.uint32).reshape(-1, 193)[:, 0]
+        by, bx = np.divmod(np.arange(got.size), w // 8)   # record order: transform blocks, raster
+        assert np.array_equal(got, exp[(by * 8 // 16) * mw + bx * 8 // 16])
+        any_fg |= bool(got.any())
+    assert any_fg
