@@ -452,7 +452,7 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
   static const char* env_v = getenv("SVC_HBMA_POOL_VARIANT");  // tuning hook
   const int variant = env_v ? atoi(env_v) : 0;
   // <range class, blocks per CTA, candidate rows per item, threads, CTAs per SM>: measured best of
-  // several shapes per class on B200 (profiles/r01_sweep_hbma_v5.md)
+  // several shapes per class on B200 (profiles/r01_sweep_hbma_v6.md)
   if (r <= 8) {
     if (variant == 1) *err = launch_pool<8, 8, 9, 128, 3>(p, st);
     else *err = launch_pool<8, 7, 17, 128, 3>(p, st);

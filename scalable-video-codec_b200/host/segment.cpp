@@ -230,19 +230,56 @@ static inline float NormL2Sqr(const float* a, const float* b, int n) {  // cv::h
   return d;
 }
 
+// Distances of all N samples to one point / of one sample to all K centres, with the samples
+// (centres) stored one coordinate per array: the loops vectorise over samples (centres) while every
+// distance keeps NormL2Sqr's operation order ((t0^2 + t1^2) + t2^2) + ..., so the floats are the
+// same as the scalar form's.
+struct Soa {
+  int n = 0, dims = 0;
+  std::vector<float> v;  // dims x n
+  void Load(const float* aos, int n_, int dims_) {
+    n = n_;
+    dims = dims_;
+    v.resize((size_t)n * dims);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < dims; ++j) v[(size_t)j * n + i] = aos[(size_t)i * dims + j];
+  }
+  const float* Row(int j) const { return v.data() + (size_t)j * n; }
+};
+
+static void DistToPoint(const Soa& s, const float* __restrict__ pt, float* __restrict__ out) {
+  const int n = s.n;
+  if (s.dims == 4) {
+    const float *x0 = s.Row(0), *x1 = s.Row(1), *x2 = s.Row(2), *x3 = s.Row(3);
+    const float p0 = pt[0], p1 = pt[1], p2 = pt[2], p3 = pt[3];
+    for (int i = 0; i < n; ++i) {
+      const float t0 = x0[i] - p0, t1 = x1[i] - p1, t2 = x2[i] - p2, t3 = x3[i] - p3;
+      out[i] = ((0.f + t0 * t0) + t1 * t1 + t2 * t2) + t3 * t3;
+    }
+    return;
+  }
+  for (int i = 0; i < n; ++i) out[i] = 0.f;
+  for (int j = 0; j < s.dims; ++j) {
+    const float* x = s.Row(j);
+    const float p = pt[j];
+    for (int i = 0; i < n; ++i) {
+      const float t = x[i] - p;
+      out[i] += t * t;
+    }
+  }
+}
+
 // k-means++ seeding with 3 trials per centre (Arthur & Vassilvitskii; OpenCV generateCentersPP)
-static void CentersPP(const float* data, int N, int dims, int K, CvRng& rng, float* out_centers,
+static void CentersPP(const float* data, const Soa& soa, int N, int dims, int K, CvRng& rng, float* out_centers,
                       std::vector<float>& buf, std::vector<int>& chosen) {
   const int trials = 3;
-  buf.resize((size_t)N * 3);
+  buf.resize((size_t)N * 4);
   chosen.resize(K);
-  float *dist = buf.data(), *tdist = dist + N, *tdist2 = tdist + N;
+  float *dist = buf.data(), *tdist = dist + N, *tdist2 = tdist + N, *raw = tdist2 + N;
   double sum0 = 0;
   chosen[0] = (int)(rng.Next() % (uint32_t)N);
-  for (int i = 0; i < N; ++i) {
-    dist[i] = NormL2Sqr(data + (size_t)i * dims, data + (size_t)chosen[0] * dims, dims);
-    sum0 += dist[i];
-  }
+  DistToPoint(soa, data + (size_t)chosen[0] * dims, dist);
+  for (int i = 0; i < N; ++i) sum0 += dist[i];
   for (int k = 1; k < K; ++k) {
     double best_sum = DBL_MAX;
     int best_center = -1;
@@ -254,10 +291,9 @@ static void CentersPP(const float* data, int N, int dims, int K, CvRng& rng, flo
         if (p <= 0) break;
       }
       double s = 0;
-      for (int i = 0; i < N; ++i) {
-        tdist2[i] = std::min(NormL2Sqr(data + (size_t)i * dims, data + (size_t)ci * dims, dims), dist[i]);
-        s += tdist2[i];
-      }
+      DistToPoint(soa, data + (size_t)ci * dims, raw);
+      for (int i = 0; i < N; ++i) tdist2[i] = std::min(raw[i], dist[i]);
+      for (int i = 0; i < N; ++i) s += tdist2[i];
       if (s < best_sum) {
         best_sum = s;
         best_center = ci;
@@ -286,6 +322,9 @@ double KMeans(const float* data, int N, int dims, int K, int max_iter, double ep
   std::vector<int> counters(K), chosen;
   std::vector<int32_t> labels(N);
   std::vector<double> dists(N);
+  Soa soa;
+  soa.Load(data, N, dims);
+  std::vector<float> dk((size_t)K * N);  // distances to centre k, all samples
   double best_compactness = DBL_MAX;
   for (int a = 0; a < attempts; ++a) {
     double compactness = 0;
@@ -293,7 +332,7 @@ double KMeans(const float* data, int N, int dims, int K, int max_iter, double ep
       double max_center_shift = iter == 0 ? DBL_MAX : 0.0;
       centers.swap(old_centers);
       if (iter == 0) {
-        CentersPP(data, N, dims, K, rng, centers.data(), ppbuf, chosen);
+        CentersPP(data, soa, N, dims, K, rng, centers.data(), ppbuf, chosen);
       } else {
         std::fill(centers.begin(), centers.end(), 0.f);
         std::fill(counters.begin(), counters.end(), 0);
@@ -357,12 +396,13 @@ double KMeans(const float* data, int N, int dims, int K, int max_iter, double ep
         }
         break;
       }
+      // assignment: nearest centre, the first one among equals (strict ">" in centre order)
+      for (int k = 0; k < K; ++k) DistToPoint(soa, centers.data() + (size_t)k * dims, dk.data() + (size_t)k * N);
       for (int i = 0; i < N; ++i) {
-        const float* s = data + (size_t)i * dims;
         int kb = 0;
-        double md = DBL_MAX;
-        for (int k = 0; k < K; ++k) {
-          const double d = NormL2Sqr(s, centers.data() + (size_t)k * dims, dims);
+        float md = dk[i];
+        for (int k = 1; k < K; ++k) {
+          const float d = dk[(size_t)k * N + i];
           if (md > d) {
             md = d;
             kb = k;
