@@ -398,6 +398,42 @@ def run_ours(a):
                "d2h_bytes_per_step": int(n_enc * (fst + mvn * 12)),
                "ms_per_step": ms_e2e, "steps": n_e2e,
                "api": "svc_session_encode (pinned host buffers; H2D | kernels | D2H pipelined)"}
+    # ---------------- SAD-bound corner of the range sweep (BASELINE config 3), N=1 only ----------
+    # The default configuration's search (r = 1) is HBM-bound; the metric also asks for the SAD
+    # rate against the integer roofline, so the search kernel is timed alone at R=64, L=1 on
+    # frames of this workload: exact byte-absdiff count (device counters) / CUDA-event time on the
+    # session stream / measured VABSDIFF4 peak of this GPU.
+    sad_roofline = None
+    if rank == 0 and world == 1 and F >= 10 and W % 16 == 0:
+        try:
+            nf = 9
+            s2 = svc.Session(svc.SessionConfig(frame_w=W, frame_h=H, mv_search_range=64, pyr_lvl_count=1,
+                                               max_batch=nf, cuda_stream=ts.cuda_stream))
+            mvn2 = s2.mv_field_w * s2.mv_field_h
+            d_mv2 = torch.empty(nf * mvn2 * 2, dtype=torch.float32, device="cuda")
+            d_mad2 = torch.empty(nf * mvn2, dtype=torch.float32, device="cuda")
+            s2.run_stage(svc.STAGE_Y_PYRAMID, d_in.data_ptr(), nf)
+            s2.run_stage(svc.STAGE_HBMA, None, nf, d_mv2.data_ptr(), d_mad2.data_ptr())  # warm-up
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            q0.record(ts)
+            for _ in range(reps):
+                s2.run_stage(svc.STAGE_HBMA, None, nf, d_mv2.data_ptr(), d_mad2.data_ptr())
+            q1.record(ts)
+            torch.cuda.synchronize()
+            ms_f = q0.elapsed_time(q1) / reps / nf
+            cand, absd = s2.hbma_work(nf)
+            peak_sad = svc.sad_peak(0)
+            sad_roofline = {"kernel": "hbma_pool_kernel (K2 at R=64, L=1: 129x129 candidates per 16x16 block)",
+                            "bound": "int-alu (VABSDIFF4)", "achieved": absd / nf / ms_f / 1e6,
+                            "peak": peak_sad / 1e9, "unit": "G byte-absdiff/s",
+                            "frac": absd / nf / (ms_f * 1e-3) / peak_sad,
+                            "gcand_per_s": cand / nf / ms_f / 1e6, "ms_per_frame": ms_f,
+                            "peak_source": "measured on this GPU (dependency-free VABSDIFF4.ACC loop)"}
+            s2.close()
+        except Exception as e:  # never let the side measurement take the headline line down
+            sad_roofline = {"error": str(e)}
     clk = clocks.stop()
 
     # ---------------- CPU baseline + exact SAD work counts (rank 0, N=1) ----------------
@@ -438,7 +474,7 @@ def run_ours(a):
                        "sharding": "contiguous frame ranges, one overlap frame, no collective",
                        "host_numa_binding": numa},
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu, "stages": stages, "sad_work": work,
+            "cpu_baseline": cpu, "stages": stages, "sad_work": work, "sad_roofline": sad_roofline,
         }
         print(json.dumps(line), flush=True)
     sess.close()
