@@ -46,6 +46,31 @@ struct PoolGeom {
   static constexpr int MAXWR = (NB * (2 * RC + 1) * NCH + 31) / 32;  // warp rounds per level
   static constexpr int EDGE = 2 * (MAXWR + NB * NCH) * NDY * 2;      // bytes of u16 edge arrays
   static constexpr int SMEM = NB * BLK + EDGE;
+  static constexpr int PA = 16;                                      // anchor pitch
+  static constexpr int kNB = NB, kNDY = NDY;
+  // copy `ph` of block j's window / its anchor block
+  __device__ static const uint8_t* window(const uint8_t* smem, int j, int ph) { return smem + j * BLK + ph * CS; }
+  __device__ static const uint8_t* anchor(const uint8_t* smem, int j) { return smem + j * BLK + 4 * CS; }
+};
+
+// Top level only (L = 1, i.e. plain EBMA): the window position does not depend on data, so the NBX
+// horizontally adjacent blocks of a CTA share ONE window (one TMA load, one copy build): it is
+// 16 NBX + 2r wide instead of NBX (16 + 2r).
+template <int RC, int NBX, int NDY>
+struct TileGeomE {
+  static constexpr int PT = (16 * NBX + 2 * RC + 15 + 15) & ~15;
+  static constexpr int ROWS = 16 + 2 * RC + NDY;
+  static constexpr int CS = ((PT * ROWS + 16 + 127) & ~127) + 32;
+  static constexpr int PA = 16 * NBX;
+  static constexpr int OFF_A = 4 * CS;                       // anchor tile: 16 rows x PA
+  static constexpr int NCH = (2 * RC + 1 + NDY - 1) / NDY;
+  static constexpr int MAXWR = (NBX * (2 * RC + 1) * NCH + 31) / 32;
+  static constexpr int EDGE = 2 * (MAXWR + NBX * NCH) * NDY * 2;
+  static constexpr int OFF_EDGE = (OFF_A + 16 * PA + 127) & ~127;
+  static constexpr int SMEM = OFF_EDGE + EDGE;
+  static constexpr int kNB = NBX, kNDY = NDY;
+  __device__ static const uint8_t* window(const uint8_t* smem, int, int ph) { return smem + ph * CS; }
+  __device__ static const uint8_t* anchor(const uint8_t* smem, int j) { return smem + OFF_A + j * 16; }
 };
 
 struct PoolLv {  // one motion block at the current level
@@ -58,7 +83,7 @@ struct PoolLv {  // one motion block at the current level
 
 // NDY vertically adjacent candidates of one candidate column: streams B+NDY-1 aligned rows
 // of the pre-shifted copy once, anchor block in registers.
-template <int B, int NDY, int PT>
+template <int B, int NDY, int PT, int PA>
 __device__ __forceinline__ void sad_column_pre(const uint8_t* __restrict__ tcol,
                                                const uint8_t* __restrict__ ablk,
                                                uint32_t (&acc)[NDY]) {
@@ -67,7 +92,7 @@ __device__ __forceinline__ void sad_column_pre(const uint8_t* __restrict__ tcol,
   uint32_t a[B][NW];
 #pragma unroll
   for (int k = 0; k < B; ++k) {
-    const uint8_t* q = ablk + k * 16;
+    const uint8_t* q = ablk + k * PA;
     if constexpr (B == 16) {
       const uint4 v = *reinterpret_cast<const uint4*>(q);
       a[k][0] = v.x; a[k][1] = v.y; a[k][2] = v.z; a[k][3] = v.w;
@@ -117,12 +142,12 @@ __device__ __forceinline__ void pool_decode(const int item, const int (&beg)[NB 
   ndy = min(v.csz, v.ncy - dy0);
 }
 
-template <int B, int RC, int NB, int NDY, int THREADS>
-__device__ __forceinline__ void pool_level(const uint8_t* smem, const PoolLv* sLv, const int (&beg)[NB + 1],
+template <int B, class G, int THREADS>
+__device__ __forceinline__ void pool_level(const uint8_t* smem, const PoolLv* sLv, const int (&beg)[G::kNB + 1],
                                            const bool top, uint32_t* sBest, uint32_t* sViol,
                                            uint16_t* sTailW, uint16_t* sHeadW, uint16_t* sTailC,
                                            uint16_t* sHeadC) {
-  using G = PoolGeom<RC, NB, NDY>;
+  constexpr int NB = G::kNB, NDY = G::kNDY;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int total = beg[NB];
   for (int base = warp * 32; base < total; base += THREADS) {  // warp-uniform trip count
@@ -136,9 +161,8 @@ __device__ __forceinline__ void pool_level(const uint8_t* smem, const PoolLv* sL
     for (int i = 0; i < NDY; ++i) acc[i] = 0;
     if (act) {
       const int sx = sLv[j].sxb + dx;
-      const uint8_t* blk = smem + j * G::BLK;
-      sad_column_pre<B, NDY, G::PT>(blk + (sx & 3) * G::CS + dy0 * G::PT + (sx & ~3),
-                                    blk + 4 * G::CS + sLv[j].aoff, acc);
+      sad_column_pre<B, NDY, G::PT, G::PA>(G::window(smem, j, sx & 3) + dy0 * G::PT + (sx & ~3),
+                                           G::anchor(smem, j) + sLv[j].aoff, acc);
     }
     // packed (sad << 16 | scan index) minimum.  top: "<=" -> the last minimum wins (index stored
     // complemented); refinement: "<" -> the first minimum wins.  The pack is an integer
@@ -360,11 +384,11 @@ hbma_pool_kernel(const __grid_constant__ PoolMaps maps, const __grid_constant__ 
 #pragma unroll
     for (int j = 0; j < NB; ++j) beg[j + 1] = beg[j] + sLv[j].n_items;
     switch (B) {
-      case 16: pool_level<16, RC, NB, NDY, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
-      case 8:  pool_level<8, RC, NB, NDY, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
-      case 4:  pool_level<4, RC, NB, NDY, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
-      case 2:  pool_level<2, RC, NB, NDY, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
-      default: pool_level<1, RC, NB, NDY, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
+      case 16: pool_level<16, G, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
+      case 8:  pool_level<8, G, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
+      case 4:  pool_level<4, G, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
+      case 2:  pool_level<2, G, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
+      default: pool_level<1, G, THREADS>(smem, sLv, beg, top, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC); break;
     }
     __syncthreads();
     if (top) {
@@ -415,6 +439,187 @@ hbma_pool_kernel(const __grid_constant__ PoolMaps maps, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// L = 1 (EstimateMotionExhaustiveSearch with 16x16 blocks, and the L = 1 column of the sweep):
+// one shared window per tile of NBX horizontally adjacent blocks, see TileGeomE.  Same work
+// items, same argmin, same zero-vector rule as pool_level's top level.
+// ---------------------------------------------------------------------------------------
+struct EbmaMaps {
+  CUtensorMap t;  // window box: PT x (16 + 2r)
+  CUtensorMap a;  // anchor tile box: 16 NBX x 16
+};
+
+template <int RC, int NBX, int NDY, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ HbmaParams p) {
+  using G = TileGeomE<RC, NBX, NDY>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ PoolLv sLv[NBX];
+  __shared__ uint32_t sBest[NBX], sViol[NBX];
+  uint16_t* sTailW = reinterpret_cast<uint16_t*>(smem + G::OFF_EDGE);
+  uint16_t* sHeadW = sTailW + G::MAXWR * NDY;
+  uint16_t* sTailC = sHeadW + G::MAXWR * NDY;
+  uint16_t* sHeadC = sTailC + NBX * G::NCH * NDY;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int r = (int)p.r;
+  const uint32_t tiles_per_row = (p.mvw + NBX - 1) / NBX, tiles_per_frame = tiles_per_row * p.mvh;
+  const uint32_t f = blockIdx.x / tiles_per_frame, ti = blockIdx.x - f * tiles_per_frame;
+  const int by = (int)(ti / tiles_per_row), bx0 = (int)(ti - (uint32_t)by * tiles_per_row) * NBX;
+  const int fw = (int)p.lay.w[0], fh = (int)p.lay.h[0];
+  const int ay = by * 16;
+  const int y0 = max(0, ay - r), y1 = min(fh - 16 + 1, ay + r + 1);
+  const int wx = max(0, bx0 * 16 - r) & ~15;  // 16-byte aligned origin of the shared window
+  const int box_h = 16 + 2 * r;
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+
+  // thread j < NBX owns block bx0 + j
+  int x0 = 0, ncx = 1, ax = 0;
+  const bool own = tid < NBX && (uint32_t)(bx0 + tid) < p.mvw;
+  if (tid < NBX) {
+    PoolLv v{};
+    if (own) {
+      ax = (bx0 + tid) * 16;
+      x0 = max(0, ax - r);
+      const int x1 = min(fw - 16 + 1, ax + r + 1);
+      ncx = x1 - x0;
+      const int ncy = y1 - y0;
+      const int nch = (ncy + NDY - 1) / NDY;
+      v.x0 = x0; v.y0 = y0; v.ncx = ncx; v.ncy = ncy;
+      v.nch = nch;
+      v.csz = (ncy + nch - 1) / nch;
+      v.sxb = x0 - wx;
+      v.aoff = 0;
+      v.magic = ncx > 1 ? 0xffffffffu / (uint32_t)ncx + 1u : 0u;
+      v.n_items = ncx * nch;
+      if (p.counters) {
+        atomicAdd(p.counters, (unsigned long long)(ncx * ncy));
+        atomicAdd(p.counters + 1, (unsigned long long)(ncx * ncy) * 256ull);
+      }
+    }
+    sLv[tid] = v;
+    sBest[tid] = 0xffffffffu;
+    sViol[tid] = 0u;
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                 "r"((uint32_t)(G::PT * box_h + 16 * G::PA)) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(&maps.t), "r"(wx), "r"(y0), "r"((int)f),
+        "r"(bar_addr) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"((uint32_t)__cvta_generic_to_shared(smem + G::OFF_A)), "l"(&maps.a), "r"(bx0 * 16), "r"(ay),
+        "r"((int)f + 1), "r"(bar_addr) : "memory");
+  }
+  __syncthreads();  // barrier initialised before anyone polls it; sLv / sBest / sViol published
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar_addr), "r"(0u) : "memory");
+    }
+  }
+  {  // three shifted copies of the shared window (see hbma_pool_kernel)
+    const int total = (G::PT / 16) * box_h;
+    for (int vb = tid - lane; vb < total; vb += 4 * THREADS) {
+      const int v0 = vb + lane;
+      uint4 v[4];
+      uint32_t nx[4];
+      uint8_t* q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        q[u] = smem + min(v0 + u * THREADS, total - 1) * 16;
+        v[u] = *reinterpret_cast<const uint4*>(q[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        nx[u] = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+        if (lane == 31) nx[u] = *reinterpret_cast<const uint32_t*>(q[u] + 16);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (v0 + u * THREADS < total) {
+#pragma unroll
+          for (int sft = 1; sft < 4; ++sft) {
+            uint4 o;
+            o.x = __funnelshift_r(v[u].x, v[u].y, 8 * sft);
+            o.y = __funnelshift_r(v[u].y, v[u].z, 8 * sft);
+            o.z = __funnelshift_r(v[u].z, v[u].w, 8 * sft);
+            o.w = __funnelshift_r(v[u].w, nx[u], 8 * sft);
+            *reinterpret_cast<uint4*>(q[u] + sft * G::CS) = o;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  int beg[NBX + 1];
+  beg[0] = 0;
+#pragma unroll
+  for (int j = 0; j < NBX; ++j) beg[j + 1] = beg[j] + sLv[j].n_items;
+  pool_level<16, G, THREADS>(smem, sLv, beg, true, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC);
+  __syncthreads();
+  {  // scan-order neighbours that were not in adjacent lanes (as in hbma_pool_kernel)
+    const int total = beg[NBX];
+    const int nwr = (total + 31) >> 5;
+    for (int e = tid; e < (nwr - 1) * NDY; e += THREADS) {
+      const int wr = 1 + e / NDY, i = e - (wr - 1) * NDY;
+      int j, c, dx, dy0, ndy;
+      pool_decode<NBX>(wr * 32, beg, sLv, j, c, dx, dy0, ndy);
+      if (dx > 0 && i < ndy && sHeadW[wr * NDY + i] > sTailW[(wr - 1) * NDY + i]) sViol[j] = 1u;
+    }
+    for (int e = tid; e < NBX * G::NCH * NDY; e += THREADS) {
+      const int jc = e / NDY, i = e - jc * NDY;
+      const int j = jc / G::NCH, c = jc - j * G::NCH;
+      const PoolLv& v = sLv[j];
+      if (v.n_items == 0 || c >= v.nch) continue;
+      if (i >= min(v.csz, v.ncy - c * v.csz)) continue;
+      uint32_t pv;
+      if (i > 0) pv = sTailC[jc * NDY + i - 1];
+      else if (c > 0) pv = sTailC[(jc - 1) * NDY + v.csz - 1];
+      else continue;
+      if (sHeadC[jc * NDY + i] > pv) sViol[j] = 1u;
+    }
+  }
+  __syncthreads();
+  if (own) {
+    const uint32_t best = sBest[tid];
+    const int idx = (int)(0xffffu - (best & 0xffffu));
+    const bool any_viol = sViol[tid] != 0u;
+    const uint64_t o = ((uint64_t)f * p.mvh + (uint32_t)by) * p.mvw + (uint32_t)(bx0 + tid);
+    if (p.mv) p.mv[o] = any_viol ? make_float2((float)(x0 + idx % ncx - ax), (float)(y0 + idx / ncx - ay))
+                                 : make_float2(0.f, 0.f);
+    if (p.mad) p.mad[o] = (float)(best >> 16) * (1.0f / 256.0f);
+  }
+}
+
+template <int RC, int NBX, int NDY, int THREADS, int MINB>
+static cudaError_t launch_ebma_tile(const HbmaParams& p, cudaStream_t st) {
+  using G = TileGeomE<RC, NBX, NDY>;
+  static_assert(G::SMEM <= 227 * 1024 && G::PT <= 256 && G::PA <= 256, "tile geometry does not fit");
+  EbmaMaps maps;
+  const uint32_t n_slots = p.n_frames + 1;
+  const uint8_t* base = p.pyr + p.lay.off[0];
+  if (!encode_box(&maps.t, base, p.lay.w[0], p.lay.h[0], p.lay.pitch[0], p.lay.slot_bytes, n_slots, G::PT,
+                  16 + 2 * p.r) ||
+      !encode_box(&maps.a, base, p.lay.w[0], p.lay.h[0], p.lay.pitch[0], p.lay.slot_bytes, n_slots, G::PA, 16))
+    return cudaErrorNotSupported;
+  auto kern = hbma_ebma_tile_kernel<RC, NBX, NDY, THREADS, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+  if (e != cudaSuccess) return e;
+  const uint64_t tiles = (uint64_t)((p.mvw + NBX - 1) / NBX) * p.mvh * p.n_frames;
+  kern<<<(uint32_t)tiles, THREADS, G::SMEM, st>>>(maps, p);
+  return cudaGetLastError();
+}
+
 template <int RC, int NB, int NDY, int THREADS, int MINB>
 static cudaError_t launch_pool(const HbmaParams& p, cudaStream_t st) {
   using G = PoolGeom<RC, NB, NDY>;
@@ -453,6 +658,21 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
   const int variant = env_v ? atoi(env_v) : 0;
   // <range class, blocks per CTA, candidate rows per item, threads, CTAs per SM>: measured best of
   // several shapes per class on B200 (profiles/r01_sweep_hbma_v6.md)
+  static const bool no_tile = getenv("SVC_HBMA_NO_EBMA_TILE") != nullptr;  // experiment hook
+  if (L == 1 && r <= 32 && !no_tile) {
+    // <range class, blocks per tile, candidate rows per item, threads, CTAs per SM>
+    if (r <= 8) {
+      if (variant == 1) *err = launch_ebma_tile<8, 5, 17, 96, 4>(p, st);
+      else *err = launch_ebma_tile<8, 5, 9, 96, 6>(p, st);
+    } else if (r <= 16) {
+      if (variant == 1) *err = launch_ebma_tile<16, 5, 11, 256, 2>(p, st);
+      else *err = launch_ebma_tile<16, 5, 11, 128, 4>(p, st);
+    } else {
+      if (variant == 1) *err = launch_ebma_tile<32, 4, 13, 224, 2>(p, st);
+      else *err = launch_ebma_tile<32, 3, 13, 128, 4>(p, st);
+    }
+    return true;
+  }
   if (r <= 8) {
     if (variant == 1) *err = launch_pool<8, 8, 9, 128, 3>(p, st);
     else *err = launch_pool<8, 7, 17, 128, 3>(p, st);

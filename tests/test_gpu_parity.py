@@ -162,6 +162,20 @@ def test_hbma_pooled_window_monotone_sequences(gpu, oracle, R, L):
             assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
 
 
+@pytest.mark.parametrize("r", [5, 8, 13, 16, 21, 32])
+@pytest.mark.parametrize("w,h", [(432, 96), (208, 64), (16, 160)])
+def test_ebma_16x16_shared_window_tiles(gpu, oracle, r, w, h):
+    """EstimateMotionExhaustiveSearch with 16x16 blocks (= HBMA with one level): the tile kernel that
+    shares one search window between horizontally adjacent blocks -- partial tiles at the right
+    frame edge, a single-column frame, windows clamped on every side, flat-patch ties."""
+    seq = SyntheticSequence(w, h, 2, seed=r * 5 + w)
+    t = oracle.y_pyramid(seq.frame(0), w, h, 1)[0]
+    a = oracle.y_pyramid(seq.frame(1), w, h, 1)[0]
+    mv, mad = gpu.EstimateMotionExhaustiveSearch(t, a, w, h, r, 16, 16)
+    emv, emad = oracle.ebma(t, a, r, 16, 16)
+    assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+
+
 def test_hbma_flat_frames_tie_break(gpu, oracle):
     z = [np.zeros((64 >> l, 96 >> l), np.uint8) for l in range(4)]
     c = [np.full((64 >> l, 96 >> l), 9, np.uint8) for l in range(4)]
