@@ -79,6 +79,9 @@ struct PoolLv {  // one motion block at the current level
   int sxb, aoff;         // byte offset of x0 inside the TMA box; of the anchor block in its box
   uint32_t magic;        // ceil(2^32 / ncx) (0 when ncx == 1)
   int n_items;           // ncx * nch (0: no block)
+  // scan order of the reference (libs/motion.cpp:312-330): index = dy * scan_ncx + scan_dx0 + dx.
+  // Equal to (ncx, 0) unless the window is searched in column stripes.
+  int scan_ncx, scan_dx0;
 };
 
 // NDY vertically adjacent candidates of one candidate column: streams B+NDY-1 aligned rows
@@ -169,9 +172,10 @@ __device__ __forceinline__ void pool_level(const uint8_t* smem, const PoolLv* sL
     // multiply-add (FMA pipe), only the minimum runs on the ALU pipe.
     uint32_t key = 0xffffffffu;
     {
-      const uint32_t idx0 = (uint32_t)(dy0 * ncx + dx);  // scan order inside the clamped window
+      const int sncx = sLv[j].scan_ncx;
+      const uint32_t idx0 = (uint32_t)(dy0 * sncx + sLv[j].scan_dx0 + dx);  // scan order inside the clamped window
       const uint32_t k0 = top ? 0xffffu - idx0 : idx0;
-      const uint32_t kstep = top ? (uint32_t)(-ncx) : (uint32_t)ncx;
+      const uint32_t kstep = top ? (uint32_t)(-sncx) : (uint32_t)sncx;
       uint32_t k[NDY];
 #pragma unroll
       for (int i = 0; i < NDY; ++i) k[i] = acc[i] * 65536u + (k0 + (uint32_t)i * kstep);
@@ -299,6 +303,8 @@ hbma_pool_kernel(const __grid_constant__ PoolMaps maps, const __grid_constant__ 
         v.aoff = ax & 15;
         v.magic = ncx > 1 ? 0xffffffffu / (uint32_t)ncx + 1u : 0u;
         v.n_items = ncx * nch;
+        v.scan_ncx = ncx;
+        v.scan_dx0 = 0;
         if (p.counters) {
           atomicAdd(p.counters, (unsigned long long)(ncx * ncy));
           atomicAdd(p.counters + 1, (unsigned long long)(ncx * ncy) * B * B);
@@ -439,6 +445,43 @@ hbma_pool_kernel(const __grid_constant__ PoolMaps maps, const __grid_constant__ 
   }
 }
 
+// three copies of ONE window (at smem, `total` 16-byte vectors) shifted left by 1, 2, 3 bytes, copy s at
+// smem + s * cs (see hbma_pool_kernel); 4 independent vectors per thread and trip
+template <int THREADS>
+__device__ __forceinline__ void tile_build_copies(uint8_t* smem, const int total, const int cs) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int vb = tid - lane; vb < total; vb += 4 * THREADS) {  // warp-uniform trip count (shuffles inside)
+    const int v0 = vb + lane;
+    uint4 v[4];
+    uint32_t nx[4];
+    uint8_t* q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      q[u] = smem + min(v0 + u * THREADS, total - 1) * 16;
+      v[u] = *reinterpret_cast<const uint4*>(q[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      nx[u] = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+      if (lane == 31) nx[u] = *reinterpret_cast<const uint32_t*>(q[u] + 16);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (v0 + u * THREADS < total) {
+#pragma unroll
+        for (int sft = 1; sft < 4; ++sft) {
+          uint4 o;
+          o.x = __funnelshift_r(v[u].x, v[u].y, 8 * sft);
+          o.y = __funnelshift_r(v[u].y, v[u].z, 8 * sft);
+          o.z = __funnelshift_r(v[u].z, v[u].w, 8 * sft);
+          o.w = __funnelshift_r(v[u].w, nx[u], 8 * sft);
+          *reinterpret_cast<uint4*>(q[u] + sft * cs) = o;
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // L = 1 (EstimateMotionExhaustiveSearch with 16x16 blocks, and the L = 1 column of the sweep):
 // one shared window per tile of NBX horizontally adjacent blocks, see TileGeomE.  Same work
@@ -493,6 +536,8 @@ hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_consta
       v.aoff = 0;
       v.magic = ncx > 1 ? 0xffffffffu / (uint32_t)ncx + 1u : 0u;
       v.n_items = ncx * nch;
+      v.scan_ncx = ncx;
+      v.scan_dx0 = 0;
       if (p.counters) {
         atomicAdd(p.counters, (unsigned long long)(ncx * ncy));
         atomicAdd(p.counters + 1, (unsigned long long)(ncx * ncy) * 256ull);
@@ -527,39 +572,7 @@ hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_consta
           : "=r"(done) : "r"(bar_addr), "r"(0u) : "memory");
     }
   }
-  {  // three shifted copies of the shared window (see hbma_pool_kernel)
-    const int total = (G::PT / 16) * box_h;
-    for (int vb = tid - lane; vb < total; vb += 4 * THREADS) {
-      const int v0 = vb + lane;
-      uint4 v[4];
-      uint32_t nx[4];
-      uint8_t* q[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        q[u] = smem + min(v0 + u * THREADS, total - 1) * 16;
-        v[u] = *reinterpret_cast<const uint4*>(q[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        nx[u] = __shfl_down_sync(0xffffffffu, v[u].x, 1);
-        if (lane == 31) nx[u] = *reinterpret_cast<const uint32_t*>(q[u] + 16);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (v0 + u * THREADS < total) {
-#pragma unroll
-          for (int sft = 1; sft < 4; ++sft) {
-            uint4 o;
-            o.x = __funnelshift_r(v[u].x, v[u].y, 8 * sft);
-            o.y = __funnelshift_r(v[u].y, v[u].z, 8 * sft);
-            o.z = __funnelshift_r(v[u].z, v[u].w, 8 * sft);
-            o.w = __funnelshift_r(v[u].w, nx[u], 8 * sft);
-            *reinterpret_cast<uint4*>(q[u] + sft * G::CS) = o;
-          }
-        }
-      }
-    }
-  }
+  tile_build_copies<THREADS>(smem, (G::PT / 16) * box_h, G::CS);
   __syncthreads();
   int beg[NBX + 1];
   beg[0] = 0;
@@ -599,6 +612,173 @@ hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_consta
                                  : make_float2(0.f, 0.f);
     if (p.mad) p.mad[o] = (float)(best >> 16) * (1.0f / 256.0f);
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// L = 1, wide ranges (r = 33 .. 112): one block per CTA, its window searched in STRIPES of CW
+// candidate columns.  A stripe's window (CW + 15 bytes wide) and its three shifted copies take
+// 40 KB instead of 100 KB for r = 64, so 4-5 CTAs share an SM and cover each other's load, build
+// and hand-over phases; best key and violation flag are carried across the stripes in shared
+// memory, as are the SADs of each stripe's last candidate column (the scan-order predecessors of
+// the next stripe's first column) and of the window's first column (successors of the last one).
+// ---------------------------------------------------------------------------------------
+template <int RC, int CW, int NDY>
+struct StripeGeomE {
+  static constexpr int PT = (16 + CW - 1 + 15 + 15) & ~15;
+  static constexpr int ROWS = 16 + 2 * RC + NDY;
+  static constexpr int CS = ((PT * ROWS + 16 + 127) & ~127) + 32;
+  static constexpr int PA = 16;
+  static constexpr int OFF_A = 4 * CS;
+  static constexpr int NCH = (2 * RC + 1 + NDY - 1) / NDY;
+  static constexpr int MAXWR = (CW * NCH + 31) / 32;
+  static constexpr int EDGE = 2 * (MAXWR + NCH) * NDY * 2;
+  static constexpr int OFF_EDGE = (OFF_A + 256 + 127) & ~127;
+  static constexpr int OFF_CARRY = (OFF_EDGE + EDGE + 15) & ~15;   // u16[2 RC + 1]: last column of the previous stripe
+  static constexpr int OFF_HEAD0 = OFF_CARRY + ((2 * (2 * RC + 1) + 15) & ~15);  // u16[2 RC + 1]: first column of the window
+  static constexpr int SMEM = OFF_HEAD0 + ((2 * (2 * RC + 1) + 15) & ~15);
+  static constexpr int kNB = 1, kNDY = NDY;
+  __device__ static const uint8_t* window(const uint8_t* smem, int, int ph) { return smem + ph * CS; }
+  __device__ static const uint8_t* anchor(const uint8_t* smem, int) { return smem + OFF_A; }
+};
+
+template <int RC, int CW, int NDY, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+hbma_ebma_stripe_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ HbmaParams p) {
+  using G = StripeGeomE<RC, CW, NDY>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ PoolLv sLv[1];
+  __shared__ uint32_t sBest[1], sViol[1];
+  uint16_t* sTailW = reinterpret_cast<uint16_t*>(smem + G::OFF_EDGE);
+  uint16_t* sHeadW = sTailW + G::MAXWR * NDY;
+  uint16_t* sTailC = sHeadW + G::MAXWR * NDY;
+  uint16_t* sHeadC = sTailC + G::NCH * NDY;
+  uint16_t* sCarry = reinterpret_cast<uint16_t*>(smem + G::OFF_CARRY);
+  uint16_t* sHead0 = reinterpret_cast<uint16_t*>(smem + G::OFF_HEAD0);
+
+  const int tid = threadIdx.x;
+  const int r = (int)p.r;
+  const uint32_t per_frame = p.mvw * p.mvh;
+  const uint32_t f = blockIdx.x / per_frame, bi = blockIdx.x - f * per_frame;
+  const int bx = (int)(bi % p.mvw), by = (int)(bi / p.mvw);
+  const int fw = (int)p.lay.w[0], fh = (int)p.lay.h[0];
+  const int ax = bx * 16, ay = by * 16;
+  const int x0 = max(0, ax - r), x1 = min(fw - 16 + 1, ax + r + 1);
+  const int y0 = max(0, ay - r), y1 = min(fh - 16 + 1, ay + r + 1);
+  const int ncx = x1 - x0, ncy = y1 - y0;
+  const int nch = (ncy + NDY - 1) / NDY, csz = (ncy + nch - 1) / nch;
+  const int box_h = 16 + 2 * r;
+  const int n_stripes = (ncx + CW - 1) / CW;
+  const int cw = (ncx + n_stripes - 1) / n_stripes;  // balanced stripes, cw <= CW
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    sBest[0] = 0xffffffffu;
+    sViol[0] = 0u;
+    if (p.counters) {
+      atomicAdd(p.counters, (unsigned long long)(ncx * ncy));
+      atomicAdd(p.counters + 1, (unsigned long long)(ncx * ncy) * 256ull);
+    }
+  }
+  for (int k = 0; k < n_stripes; ++k) {
+    const int xs = x0 + k * cw, ncs = min(cw, ncx - k * cw);
+    if (tid == 0) {
+      PoolLv v{};
+      v.x0 = xs; v.y0 = y0; v.ncx = ncs; v.ncy = ncy;
+      v.nch = nch; v.csz = csz;
+      v.sxb = xs & 15;
+      v.aoff = 0;
+      v.magic = ncs > 1 ? 0xffffffffu / (uint32_t)ncs + 1u : 0u;
+      v.n_items = ncs * nch;
+      v.scan_ncx = ncx;
+      v.scan_dx0 = k * cw;
+      sLv[0] = v;
+      // the previous stripe's window was read through the generic proxy (all threads are past the
+      // barrier that closed it)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                   "r"((uint32_t)(G::PT * box_h + (k == 0 ? 256 : 0))) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(&maps.t), "r"(xs & ~15), "r"(y0), "r"((int)f),
+          "r"(bar_addr) : "memory");
+      if (k == 0)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(smem + G::OFF_A)), "l"(&maps.a), "r"(ax), "r"(ay),
+            "r"((int)f + 1), "r"(bar_addr) : "memory");
+    }
+    __syncthreads();  // barrier initialised / re-armed before anyone polls it; sLv published
+    {
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar_addr), "r"((uint32_t)(k & 1)) : "memory");
+      }
+    }
+    tile_build_copies<THREADS>(smem, (G::PT / 16) * box_h, G::CS);
+    __syncthreads();
+    int beg[2] = {0, ncs * nch};
+    pool_level<16, G, THREADS>(smem, sLv, beg, true, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC);
+    __syncthreads();
+    {  // scan-order neighbours that were not in adjacent lanes
+      const int nwr = (beg[1] + 31) >> 5;
+      for (int e = tid; e < (nwr - 1) * NDY; e += THREADS) {  // warp-round boundaries inside the stripe
+        const int wr = 1 + e / NDY, i = e - (wr - 1) * NDY;
+        int j, c, dx, dy0, ndy;
+        pool_decode<1>(wr * 32, beg, sLv, j, c, dx, dy0, ndy);
+        if (dx > 0 && i < ndy && sHeadW[wr * NDY + i] > sTailW[(wr - 1) * NDY + i]) sViol[0] = 1u;
+      }
+      for (int dy = tid; dy < ncy; dy += THREADS) {  // first column of the stripe, row dy
+        const int c = dy / csz, i = dy - c * csz;
+        const uint32_t head = sHeadC[c * NDY + i];
+        if (k > 0) {
+          if (head > sCarry[dy]) sViol[0] = 1u;  // predecessor: last column of the previous stripe, same row
+        } else {
+          sHead0[dy] = (uint16_t)head;
+        }
+        if (k == n_stripes - 1 && dy > 0) {
+          // predecessor of the window's first column: its last column, one row up
+          const int cp = (dy - 1) / csz, ip = (dy - 1) - cp * csz;
+          if (sHead0[dy] > sTailC[cp * NDY + ip]) sViol[0] = 1u;
+        }
+        sCarry[dy] = sTailC[c * NDY + i];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const uint32_t best = sBest[0];
+    const int idx = (int)(0xffffu - (best & 0xffffu));
+    const bool any_viol = sViol[0] != 0u;
+    const uint64_t o = (uint64_t)f * per_frame + bi;
+    if (p.mv) p.mv[o] = any_viol ? make_float2((float)(x0 + idx % ncx - ax), (float)(y0 + idx / ncx - ay))
+                                 : make_float2(0.f, 0.f);
+    if (p.mad) p.mad[o] = (float)(best >> 16) * (1.0f / 256.0f);
+  }
+}
+
+template <int RC, int CW, int NDY, int THREADS, int MINB>
+static cudaError_t launch_ebma_stripe(const HbmaParams& p, cudaStream_t st) {
+  using G = StripeGeomE<RC, CW, NDY>;
+  static_assert(G::SMEM <= 227 * 1024 && G::PT <= 256 && 16 + 2 * RC <= 256, "stripe geometry does not fit");
+  EbmaMaps maps;
+  const uint32_t n_slots = p.n_frames + 1;
+  const uint8_t* base = p.pyr + p.lay.off[0];
+  if (!encode_box(&maps.t, base, p.lay.w[0], p.lay.h[0], p.lay.pitch[0], p.lay.slot_bytes, n_slots, G::PT,
+                  16 + 2 * p.r) ||
+      !encode_box(&maps.a, base, p.lay.w[0], p.lay.h[0], p.lay.pitch[0], p.lay.slot_bytes, n_slots, 16, 16))
+    return cudaErrorNotSupported;
+  auto kern = hbma_ebma_stripe_kernel<RC, CW, NDY, THREADS, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+  if (e != cudaSuccess) return e;
+  const uint64_t n_blocks = (uint64_t)p.mvw * p.mvh * p.n_frames;
+  kern<<<(uint32_t)n_blocks, THREADS, G::SMEM, st>>>(maps, p);
+  return cudaGetLastError();
 }
 
 template <int RC, int NBX, int NDY, int THREADS, int MINB>
@@ -647,7 +827,7 @@ static cudaError_t launch_pool(const HbmaParams& p, cudaStream_t st) {
 bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
   static const bool off = getenv("SVC_HBMA_NO_POOL") != nullptr;  // experiment hook
   const uint32_t L = p.lay.levels, r = p.r;
-  if (off || p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > 64) return false;
+  if (off || p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > (L == 1 ? 112u : 64u)) return false;
   if ((uint64_t)p.mvw * p.mvh * p.n_frames > 0x7fffffffull) return false;
   // Deep pyramids with a small top-level range are dominated by the per-level fixed costs (TMA
   // round trip, copy build, barriers) of the small coarse levels: the warp-per-block window
@@ -657,8 +837,16 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
   static const char* env_v = getenv("SVC_HBMA_POOL_VARIANT");  // tuning hook
   const int variant = env_v ? atoi(env_v) : 0;
   // <range class, blocks per CTA, candidate rows per item, threads, CTAs per SM>: measured best of
-  // several shapes per class on B200 (profiles/r01_sweep_hbma_v7.md)
+  // several shapes per class on B200 (profiles/r01_sweep_hbma_v8.md)
   static const bool no_tile = getenv("SVC_HBMA_NO_EBMA_TILE") != nullptr;  // experiment hook
+  if (L == 1 && r > 32 && !no_tile) {
+    // <range class, stripe width in candidate columns, candidate rows per item, threads, CTAs per SM>
+    if (variant == 1) *err = launch_ebma_stripe<64, 43, 13, 128, 4>(p, st);
+    else if (variant == 4) return false;  // the per-block kernels below / in k_hbma.cu
+    else if (r > 64) *err = launch_ebma_stripe<112, 65, 13, 128, 2>(p, st);
+    else *err = launch_ebma_stripe<64, 65, 13, 128, 3>(p, st);
+    return true;
+  }
   if (L == 1 && r <= 32 && !no_tile) {
     // <range class, blocks per tile, candidate rows per item, threads, CTAs per SM>
     if (r <= 8) {

@@ -140,7 +140,7 @@ def test_hbma_pooled_window_path_vs_oracle(gpu, oracle, L, R, w, h, monkeypatch)
     assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
 
 
-@pytest.mark.parametrize("R,L", [(8, 1), (16, 1), (32, 1), (64, 1), (64, 2)])
+@pytest.mark.parametrize("R,L", [(8, 1), (16, 1), (32, 1), (40, 1), (64, 1), (100, 1), (64, 2)])
 def test_hbma_pooled_window_monotone_sequences(gpu, oracle, R, L):
     """Top-level zero-vector rule (libs/motion.cpp:333-337) on the pooled kernel: horizontal /
     vertical ramps and constant frames make the SAD sequence non-increasing over whole windows
@@ -162,12 +162,13 @@ def test_hbma_pooled_window_monotone_sequences(gpu, oracle, R, L):
             assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
 
 
-@pytest.mark.parametrize("r", [5, 8, 13, 16, 21, 32])
+@pytest.mark.parametrize("r", [5, 8, 13, 16, 21, 32, 33, 47, 64, 80, 112])
 @pytest.mark.parametrize("w,h", [(432, 96), (208, 64), (16, 160)])
 def test_ebma_16x16_shared_window_tiles(gpu, oracle, r, w, h):
     """EstimateMotionExhaustiveSearch with 16x16 blocks (= HBMA with one level): the tile kernel that
-    shares one search window between horizontally adjacent blocks -- partial tiles at the right
-    frame edge, a single-column frame, windows clamped on every side, flat-patch ties."""
+    shares one search window between horizontally adjacent blocks (r <= 32) and the kernel that
+    searches a wide window in column stripes (r > 32) -- partial tiles at the right frame edge, a
+    single-column frame, 1..5 stripes, windows clamped on every side, flat-patch ties."""
     seq = SyntheticSequence(w, h, 2, seed=r * 5 + w)
     t = oracle.y_pyramid(seq.frame(0), w, h, 1)[0]
     a = oracle.y_pyramid(seq.frame(1), w, h, 1)[0]
