@@ -1,5 +1,10 @@
-// k_hbma_pool.cu -- K2, large search ranges (16x16 blocks, top-level range r = 5..64): the
-// SAD-bound regime of the range / level sweep (BASELINE config 3).
+// k_hbma_pool.cu -- K2, large search ranges (16x16 blocks, top-level range r >= 5): the
+// SAD-bound regime of the range / level sweep (BASELINE config 3).  Three kernels:
+//   hbma_pool_kernel         any pyramid depth, r = 5..64: per-block windows, pooled work items
+//   hbma_ebma_tile_kernel    L = 1, r <= 32: one shared window per tile of adjacent blocks
+//   hbma_ebma_stripe_kernel  L = 1, r = 33..112: one block per CTA, window in column stripes
+// (L = 1 is EstimateMotionExhaustiveSearch, libs/motion.cpp:268-340; the window position is then
+// not data dependent).  All three share the work-item code (pool_level / sad_column_pre).
 //
 // Same arithmetic and scan-order rules as k_hbma.cu (reference libs/motion.cpp:268-465,
 // 691-749); this file only changes how the work is laid out on the SM, to keep the
