@@ -117,9 +117,14 @@ int main(int argc, char** argv) {
       const svc::ShardedStats s = svc::EncodeFileSharded(cfg, svc::VideoProperties{width, height, frames}, path,
                                                          out_path, devices);
       if (verbose)
-        std::fprintf(stderr, "encoded %llu frames on %zu device(s) in %.3f s (%.1f frames/s)\n",
+        std::fprintf(stderr,
+                     "encoded %llu frames on %zu device(s) in %.3f s (%.1f frames/s overall)\n"
+                     "  slowest shard: set-up %.3f s, read %.3f s, encode + block types %.3f s (%.1f frames/s "
+                     "aggregate), write %.3f s\n",
                      (unsigned long long)s.frames_encoded, devices.size(), s.seconds,
-                     s.seconds > 0 ? s.frames_encoded / s.seconds : 0.0);
+                     s.seconds > 0 ? s.frames_encoded / s.seconds : 0.0, s.setup_seconds, s.read_seconds,
+                     s.encode_seconds, s.encode_seconds > 0 ? s.frames_encoded / s.encode_seconds : 0.0,
+                     s.write_seconds);
     } catch (const std::exception& e) {
       std::fprintf(stderr, "svc_encoder: %s\n", e.what());
       return EXIT_FAILURE;

@@ -510,7 +510,7 @@ hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_consta
   uint16_t* sTailC = sHeadW + G::MAXWR * NDY;
   uint16_t* sHeadC = sTailC + NBX * G::NCH * NDY;
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int r = (int)p.r;
   const uint32_t tiles_per_row = (p.mvw + NBX - 1) / NBX, tiles_per_frame = tiles_per_row * p.mvh;
   const uint32_t f = blockIdx.x / tiles_per_frame, ti = blockIdx.x - f * tiles_per_frame;

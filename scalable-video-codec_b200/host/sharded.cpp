@@ -5,6 +5,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -54,9 +55,16 @@ void pwrite_all(int fd, const uchar* p, size_t n, uint64_t off) {
   }
 }
 
+double now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// times[]: set-up, read, encode (+ block types), write
 void run_shard(const EncoderConfig& cfg, const VideoProperties& vp, const std::string& in_path, int out_fd,
-               int device, ShardRange r, const BlockTypeFn& classify, uint64_t* encoded) {
+               int device, ShardRange r, const BlockTypeFn& classify, uint64_t* encoded,
+               std::array<double, 4>* times) {
   if (r.enc_hi <= r.enc_lo) return;
+  double t0 = now();
   svc_session_config c{};
   c.struct_size = sizeof(c);
   c.frame_w = vp.frame_w; c.frame_h = vp.frame_h;
@@ -85,9 +93,13 @@ void run_shard(const EncoderConfig& cfg, const VideoProperties& vp, const std::s
   if (fseeko(in, (off_t)((uint64_t)r.in_lo * info.frame_in_bytes), SEEK_SET) != 0)
     throw Error(SVC_ERR_INVALID_ARG, "seek failed");
   uint next_in = r.in_lo, next_enc = r.enc_lo;
+  (*times)[0] = now() - t0;
   while (next_in < r.in_hi) {
     const uint n = (uint)std::min<size_t>(B, r.in_hi - next_in);
+    t0 = now();
     if (std::fread(h_in.p, info.frame_in_bytes, n, in) != n) throw Error(SVC_ERR_INVALID_ARG, "short read");
+    (*times)[1] += now() - t0;
+    t0 = now();
     uint n_enc = 0;
     check(svc_session_encode(s, static_cast<const uint8_t*>(h_in.p), n, static_cast<float*>(h_mv.p),
                              static_cast<float*>(h_mad.p), static_cast<uint8_t*>(h_st.p), nullptr, &n_enc));
@@ -109,9 +121,12 @@ void run_shard(const EncoderConfig& cfg, const VideoProperties& vp, const std::s
                                     cfg.mv_block_w, cfg.mv_block_h, info.mv_field_w, bt.data()));
       }
     }
+    (*times)[2] += now() - t0;
+    t0 = now();
     // encoded frame t (anchor = input frame t) lives at 32 + (t-1) * frame_stream_bytes
     pwrite_all(out_fd, static_cast<uchar*>(h_st.p), (size_t)n_enc * info.frame_stream_bytes,
                32 + (uint64_t)(next_enc - 1) * info.frame_stream_bytes);
+    (*times)[3] += now() - t0;
     next_in += n;
     next_enc += n_enc;
     *encoded += n_enc;
@@ -139,11 +154,12 @@ ShardedStats EncodeFileSharded(const EncoderConfig& cfg, const VideoProperties& 
   std::vector<std::thread> threads;
   std::vector<std::exception_ptr> errors(devices.size());
   std::vector<uint64_t> encoded(devices.size(), 0);
+  std::vector<std::array<double, 4>> times(devices.size(), std::array<double, 4>{0, 0, 0, 0});
   const auto t0 = std::chrono::steady_clock::now();
   for (size_t g = 0; g < devices.size(); ++g)
     threads.emplace_back([&, g] {
       try {
-        run_shard(cfg, vidprops, in_path, fd, devices[g], ranges[g], classify, &encoded[g]);
+        run_shard(cfg, vidprops, in_path, fd, devices[g], ranges[g], classify, &encoded[g], &times[g]);
       } catch (...) {
         errors[g] = std::current_exception();
       }
@@ -154,6 +170,12 @@ ShardedStats EncodeFileSharded(const EncoderConfig& cfg, const VideoProperties& 
   for (auto& e : errors)
     if (e) std::rethrow_exception(e);
   for (auto n : encoded) stats.frames_encoded += n;
+  for (const auto& t : times) {
+    stats.setup_seconds = std::max(stats.setup_seconds, t[0]);
+    stats.read_seconds = std::max(stats.read_seconds, t[1]);
+    stats.encode_seconds = std::max(stats.encode_seconds, t[2]);
+    stats.write_seconds = std::max(stats.write_seconds, t[3]);
+  }
   return stats;
 }
 

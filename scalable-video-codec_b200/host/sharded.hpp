@@ -7,6 +7,7 @@
 #ifndef SVC_B200_HOST_SHARDED_HPP
 #define SVC_B200_HOST_SHARDED_HPP
 
+#include <array>
 #include <string>
 #include <vector>
 
@@ -23,7 +24,11 @@ std::vector<ShardRange> ShardFrameRanges(uint n_input_frames, uint world);
 
 struct ShardedStats {
   uint64_t frames_encoded = 0;
-  double seconds = 0;  // wall clock of the parallel section
+  double seconds = 0;        // wall clock of the parallel section (set-up included)
+  double setup_seconds = 0;  // slowest shard: CUDA context, session, pinned staging buffers
+  double read_seconds = 0;   // slowest shard: reading input frames
+  double encode_seconds = 0; // slowest shard: svc_session_encode (H2D | kernels | D2H) + block-type stages
+  double write_seconds = 0;  // slowest shard: writing the records
 };
 
 // Encodes `in_path` (vidprops.frame_count raw BGR frames) into `out_path` (header +
