@@ -119,12 +119,12 @@ int main(int argc, char** argv) {
       if (verbose)
         std::fprintf(stderr,
                      "encoded %llu frames on %zu device(s) in %.3f s (%.1f frames/s overall)\n"
-                     "  slowest shard: set-up %.3f s, read %.3f s, encode + block types %.3f s (%.1f frames/s "
-                     "aggregate), write %.3f s\n",
+                     "  slowest shard: set-up %.3f s, then %.1f frames/s; busy time: read %.3f s, GPU encode + "
+                     "block types %.3f s, write %.3f s (block types and writes overlap the next batch)\n",
                      (unsigned long long)s.frames_encoded, devices.size(), s.seconds,
-                     s.seconds > 0 ? s.frames_encoded / s.seconds : 0.0, s.setup_seconds, s.read_seconds,
-                     s.encode_seconds, s.encode_seconds > 0 ? s.frames_encoded / s.encode_seconds : 0.0,
-                     s.write_seconds);
+                     s.seconds > 0 ? s.frames_encoded / s.seconds : 0.0, s.setup_seconds,
+                     s.seconds > s.setup_seconds ? s.frames_encoded / (s.seconds - s.setup_seconds) : 0.0,
+                     s.read_seconds, s.encode_seconds, s.write_seconds);
     } catch (const std::exception& e) {
       std::fprintf(stderr, "svc_encoder: %s\n", e.what());
       return EXIT_FAILURE;

@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstring>
 #include <exception>
+#include <atomic>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 #include "../../include/svc_b200.h"
@@ -78,7 +80,18 @@ void run_shard(const EncoderConfig& cfg, const VideoProperties& vp, const std::s
   svc_session_info info{};
   check(svc_session_info_get(s, &info));
   const size_t B = info.max_batch, mvn = (size_t)info.mv_field_w * info.mv_field_h;
-  Pinned h_in(B * info.frame_in_bytes), h_st(B * info.frame_stream_bytes), h_mv(B * mvn * 8), h_mad(B * mvn * 4);
+  // Two sets of output staging: while the GPU encodes batch k+1 into one set, a post thread labels
+  // the motion fields of batch k (block-type stages, libs/encoder.cpp:491-624), patches the labels
+  // into its records and writes them out of the other set.
+  Pinned h_in(B * info.frame_in_bytes);
+  struct OutSet {
+    Pinned st, mv, mad;
+    std::thread post;
+    std::exception_ptr error;
+    OutSet(size_t b, size_t fst, size_t mvn) : st(b * fst), mv(b * mvn * 8), mad(b * mvn * 4) {}
+  };
+  OutSet sets[2] = {OutSet(B, info.frame_stream_bytes, mvn), OutSet(B, info.frame_stream_bytes, mvn)};
+  std::mutex post_mu;  // post sections run one at a time, in batch order (the stage's scratch is shared)
   std::vector<uint> bt(mvn), batch_types;
   std::unique_ptr<BlockTypeStage> stage;
   if (!classify && cfg.segment) {
@@ -94,43 +107,70 @@ void run_shard(const EncoderConfig& cfg, const VideoProperties& vp, const std::s
     throw Error(SVC_ERR_INVALID_ARG, "seek failed");
   uint next_in = r.in_lo, next_enc = r.enc_lo;
   (*times)[0] = now() - t0;
-  while (next_in < r.in_hi) {
+  std::atomic<uint64_t> post_ns{0}, write_ns{0};
+  struct Joiner {  // declared last: on an exception the post threads are joined before anything they use dies
+    OutSet* s;
+    ~Joiner() {
+      for (int i = 0; i < 2; ++i)
+        if (s[i].post.joinable()) s[i].post.join();
+    }
+  } joiner{sets};
+  for (uint k = 0; next_in < r.in_hi; ++k) {
+    OutSet& o = sets[k & 1];
+    if (o.post.joinable()) o.post.join();  // this set's previous batch is on disk
+    if (o.error) std::rethrow_exception(o.error);
     const uint n = (uint)std::min<size_t>(B, r.in_hi - next_in);
     t0 = now();
     if (std::fread(h_in.p, info.frame_in_bytes, n, in) != n) throw Error(SVC_ERR_INVALID_ARG, "short read");
     (*times)[1] += now() - t0;
     t0 = now();
     uint n_enc = 0;
-    check(svc_session_encode(s, static_cast<const uint8_t*>(h_in.p), n, static_cast<float*>(h_mv.p),
-                             static_cast<float*>(h_mad.p), static_cast<uint8_t*>(h_st.p), nullptr, &n_enc));
-    if (stage && n_enc) {  // per-frame generators depend on the global frame index only
-      batch_types.resize((size_t)n_enc * mvn);
-      stage->Run(reinterpret_cast<const Vec2f*>(h_mv.p), n_enc, next_enc - 1, batch_types.data());
-    }
-    for (uint i = 0; i < n_enc; ++i) {
-      uchar* rec = static_cast<uchar*>(h_st.p) + (size_t)i * info.frame_stream_bytes;
-      if (stage) {
-        check(svc_patch_block_types(rec, vp.frame_w, vp.frame_h, cfg.transform_block_w, cfg.transform_block_h, 3,
-                                    cfg.mv_block_w, cfg.mv_block_h, info.mv_field_w,
-                                    batch_types.data() + (size_t)i * mvn));
-      } else if (classify) {
-        std::fill(bt.begin(), bt.end(), 0u);
-        classify(reinterpret_cast<const Vec2f*>(static_cast<float*>(h_mv.p) + (size_t)i * mvn * 2),
-                 static_cast<float*>(h_mad.p) + (size_t)i * mvn, info.mv_field_w, info.mv_field_h, bt.data());
-        check(svc_patch_block_types(rec, vp.frame_w, vp.frame_h, cfg.transform_block_w, cfg.transform_block_h, 3,
-                                    cfg.mv_block_w, cfg.mv_block_h, info.mv_field_w, bt.data()));
-      }
-    }
+    check(svc_session_encode(s, static_cast<const uint8_t*>(h_in.p), n, static_cast<float*>(o.mv.p),
+                             static_cast<float*>(o.mad.p), static_cast<uint8_t*>(o.st.p), nullptr, &n_enc));
     (*times)[2] += now() - t0;
-    t0 = now();
-    // encoded frame t (anchor = input frame t) lives at 32 + (t-1) * frame_stream_bytes
-    pwrite_all(out_fd, static_cast<uchar*>(h_st.p), (size_t)n_enc * info.frame_stream_bytes,
-               32 + (uint64_t)(next_enc - 1) * info.frame_stream_bytes);
-    (*times)[3] += now() - t0;
+    const uint first_enc = next_enc;
+    o.post = std::thread([&, n_enc, first_enc, po = &o] {
+      try {
+        std::lock_guard<std::mutex> lock(post_mu);
+        const double p0 = now();
+        if (stage && n_enc) {  // per-frame generators depend on the global frame index only
+          batch_types.resize((size_t)n_enc * mvn);
+          stage->Run(reinterpret_cast<const Vec2f*>(po->mv.p), n_enc, first_enc - 1, batch_types.data());
+        }
+        for (uint i = 0; i < n_enc; ++i) {
+          uchar* rec = static_cast<uchar*>(po->st.p) + (size_t)i * info.frame_stream_bytes;
+          if (stage) {
+            check(svc_patch_block_types(rec, vp.frame_w, vp.frame_h, cfg.transform_block_w, cfg.transform_block_h, 3,
+                                        cfg.mv_block_w, cfg.mv_block_h, info.mv_field_w,
+                                        batch_types.data() + (size_t)i * mvn));
+          } else if (classify) {
+            std::fill(bt.begin(), bt.end(), 0u);
+            classify(reinterpret_cast<const Vec2f*>(static_cast<float*>(po->mv.p) + (size_t)i * mvn * 2),
+                     static_cast<float*>(po->mad.p) + (size_t)i * mvn, info.mv_field_w, info.mv_field_h, bt.data());
+            check(svc_patch_block_types(rec, vp.frame_w, vp.frame_h, cfg.transform_block_w, cfg.transform_block_h, 3,
+                                        cfg.mv_block_w, cfg.mv_block_h, info.mv_field_w, bt.data()));
+          }
+        }
+        const double p1 = now();
+        // encoded frame t (anchor = input frame t) lives at 32 + (t-1) * frame_stream_bytes
+        pwrite_all(out_fd, static_cast<uchar*>(po->st.p), (size_t)n_enc * info.frame_stream_bytes,
+                   32 + (uint64_t)(first_enc - 1) * info.frame_stream_bytes);
+        post_ns += (uint64_t)((p1 - p0) * 1e9);
+        write_ns += (uint64_t)((now() - p1) * 1e9);
+      } catch (...) {
+        po->error = std::current_exception();
+      }
+    });
     next_in += n;
     next_enc += n_enc;
     *encoded += n_enc;
   }
+  for (auto& o : sets) {
+    if (o.post.joinable()) o.post.join();
+    if (o.error) std::rethrow_exception(o.error);
+  }
+  (*times)[2] += post_ns.load() * 1e-9;   // block-type stages + patching (overlapped with the GPU batches)
+  (*times)[3] += write_ns.load() * 1e-9;  // (overlapped too)
 }
 
 }  // namespace

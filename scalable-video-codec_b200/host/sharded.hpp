@@ -27,6 +27,7 @@ struct ShardedStats {
   double seconds = 0;        // wall clock of the parallel section (set-up included)
   double setup_seconds = 0;  // slowest shard: CUDA context, session, pinned staging buffers
   double read_seconds = 0;   // slowest shard: reading input frames
+  // the next two run on a post thread, overlapped with the following batch's read + encode
   double encode_seconds = 0; // slowest shard: svc_session_encode (H2D | kernels | D2H) + block-type stages
   double write_seconds = 0;  // slowest shard: writing the records
 };
