@@ -49,6 +49,7 @@ def parse():
                     help="input frames in the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sad", action="store_true", help="skip the SAD-roofline side measurement (R=32/64, L=1)")
     return ap.parse_args()
 
 
@@ -404,7 +405,7 @@ def run_ours(a):
     # frames of this workload: exact byte-absdiff count (device counters) / CUDA-event time on the
     # session stream / measured VABSDIFF4 peak of this GPU.
     sad_roofline = None
-    if rank == 0 and world == 1 and F >= 10 and W % 16 == 0:
+    if rank == 0 and world == 1 and F >= 10 and W % 16 == 0 and not a.no_sad:
         try:
             nf = 9
             peak_sad = svc.sad_peak(0)
