@@ -55,3 +55,35 @@ def test_random_session_config(gpu, oracle, cfg):
             e = exp.view(np.uint32).reshape(-1, rec)
             assert np.array_equal(g[:, 0], e[:, 0]), (cfg, i)
             assert np.abs(g[:, 1:].view(np.float32) - e[:, 1:].view(np.float32)).max() <= DCT_TOL, (cfg, i)
+
+
+def _wide_configs(n, seed):
+    """16x16 blocks with top-level ranges 5..70: the pooled / shared-window / column-striped kernels
+    of k_hbma_pool.cu in session mode (several frame pairs per launch, frames smaller than the window)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        L = int(rng.choice([1, 1, 1, 2, 2, 3]))
+        r_top = int(rng.choice([5, 7, 8, 11, 16, 19, 32, 33, 40, 64, 70]))
+        if L > 1 and r_top > 64:
+            continue
+        R = r_top * (1 << (L - 1)) + int(rng.integers(0, 1 << (L - 1)))
+        w = int(rng.integers(16, 280))
+        h = int(rng.integers(16, 200))
+        out.append((w, h, L, R, int(rng.integers(2, 5)), int(rng.integers(1, 4))))
+    return out
+
+
+@pytest.mark.parametrize("cfg", _wide_configs(16, 77))
+def test_random_wide_range_session(gpu, oracle, cfg):
+    w, h, L, R, n, batch = cfg
+    frames = SyntheticSequence(w, h, n, seed=w * 17 + h, n_rects=3).frames()
+    sc = gpu.SessionConfig(frame_w=w, frame_h=h, mv_search_range=R, pyr_lvl_count=L, max_batch=batch)
+    with gpu.Session(sc) as s:
+        pw, ph = s.padded_w, s.padded_h
+        mv, mad, _ = s.encode(frames)
+        pyr = [oracle.y_pyramid(f, pw, ph, L) for f in frames]
+        for i in range(1, n):
+            emv, emad = oracle.hbma(pyr[i - 1], pyr[i], R)
+            assert np.array_equal(mv[i - 1], emv), (cfg, i)
+            assert np.array_equal(mad[i - 1], emad), (cfg, i)
