@@ -5,6 +5,8 @@
 #include "encoder.hpp"
 
 #include <cstring>
+#include <exception>
+#include <thread>
 
 #include "../../include/svc_b200.h"
 
@@ -81,10 +83,13 @@ Encoder::Encoder(const EncoderConfig& cfg, const VideoProperties& vidprops,
   frame_in_bytes_ = info.frame_in_bytes;
   const size_t B = info.max_batch, mvn = (size_t)mv_field_w_ * mv_field_h_;
   h_in_ = static_cast<uchar*>(svc_host_alloc(B * frame_in_bytes_));
-  h_stream_ = static_cast<uchar*>(svc_host_alloc(B * frame_stream_bytes_));
-  h_mv_ = static_cast<float*>(svc_host_alloc(B * mvn * 2 * sizeof(float)));
-  h_mad_ = static_cast<float*>(svc_host_alloc(B * mvn * sizeof(float)));
-  if (!h_in_ || !h_stream_ || !h_mv_ || !h_mad_) throw Error(SVC_ERR_CUDA, "pinned allocation failed");
+  for (int k = 0; k < 2; ++k) {
+    h_stream_[k] = static_cast<uchar*>(svc_host_alloc(B * frame_stream_bytes_));
+    h_mv_[k] = static_cast<float*>(svc_host_alloc(B * mvn * 2 * sizeof(float)));
+    h_mad_[k] = static_cast<float*>(svc_host_alloc(B * mvn * sizeof(float)));
+    if (!h_stream_[k] || !h_mv_[k] || !h_mad_[k]) throw Error(SVC_ERR_CUDA, "pinned allocation failed");
+  }
+  if (!h_in_) throw Error(SVC_ERR_CUDA, "pinned allocation failed");
   if (!classify_ && cfg_.segment) {
     SegmentConfig sc = cfg_.seg;
     sc.mv_block_w = cfg_.mv_block_w;
@@ -95,9 +100,11 @@ Encoder::Encoder(const EncoderConfig& cfg, const VideoProperties& vidprops,
 
 Encoder::~Encoder() {
   svc_host_free(h_in_);
-  svc_host_free(h_stream_);
-  svc_host_free(h_mv_);
-  svc_host_free(h_mad_);
+  for (int k = 0; k < 2; ++k) {
+    svc_host_free(h_stream_[k]);
+    svc_host_free(h_mv_[k]);
+    svc_host_free(h_mad_[k]);
+  }
   svc_session_destroy(session_);
 }
 
@@ -116,7 +123,13 @@ void Encoder::operator()() {
   svc_session_info info{};
   check(svc_session_info_get(session_, &info));
   Frame frame;
-  while (true) {
+  std::thread post;  // at most one alive: batch k's labels / patching / pushes, in frame order
+  std::exception_ptr post_error;
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } joiner{post};
+  for (uint k = 0;; ++k) {
     // block for one frame, then take whatever else is already queued (<= max_batch)
     if (!in_queue_.Pop(frame)) break;
     uint n = 0;
@@ -125,30 +138,46 @@ void Encoder::operator()() {
       std::memcpy(h_in_ + (size_t)n * frame_in_bytes_, frame.data(), frame_in_bytes_);
       ++n;
     } while (n < info.max_batch && in_queue_.TryPop(frame));
+    const int set = (int)(k & 1);
+    uchar* h_stream = h_stream_[set];
+    float* h_mv = h_mv_[set];
+    float* h_mad = h_mad_[set];
     uint n_enc = 0;
-    check(svc_session_encode(session_, h_in_, n, h_mv_, h_mad_, h_stream_, nullptr, &n_enc));
-    if (stage_ && n_enc) {  // libs/encoder.cpp:491-624 for the whole batch, on worker threads
-      batch_types.resize((size_t)n_enc * mvn);
-      stage_->Run(reinterpret_cast<const Vec2f*>(h_mv_), n_enc, frames_encoded_, batch_types.data());
-    }
-    for (uint i = 0; i < n_enc; ++i) {
-      uchar* rec = h_stream_ + (size_t)i * frame_stream_bytes_;
-      if (stage_) {
-        check(svc_patch_block_types(rec, vidprops_.frame_w, vidprops_.frame_h, cfg_.transform_block_w,
-                                    cfg_.transform_block_h, 3, cfg_.mv_block_w, cfg_.mv_block_h,
-                                    mv_field_w_, batch_types.data() + (size_t)i * mvn));
-      } else if (classify_) {
-        std::fill(block_types.begin(), block_types.end(), 0u);  // BLOCK_TYPE_BACKGROUND, libs/encoder.cpp:549-551
-        classify_(reinterpret_cast<const Vec2f*>(h_mv_ + (size_t)i * mvn * 2), h_mad_ + (size_t)i * mvn,
-                  mv_field_w_, mv_field_h_, block_types.data());
-        check(svc_patch_block_types(rec, vidprops_.frame_w, vidprops_.frame_h, cfg_.transform_block_w,
-                                    cfg_.transform_block_h, 3, cfg_.mv_block_w, cfg_.mv_block_h,
-                                    mv_field_w_, block_types.data()));
+    check(svc_session_encode(session_, h_in_, n, h_mv, h_mad, h_stream, nullptr, &n_enc));
+    // batch k-1 is out of the other set before batch k+1 may overwrite it, and frames leave in order
+    if (post.joinable()) post.join();
+    if (post_error) std::rethrow_exception(post_error);
+    const uint64_t first_frame = frames_encoded_;
+    frames_encoded_ += n_enc;
+    post = std::thread([&, n_enc, first_frame, h_stream, h_mv, h_mad] {
+      try {
+        if (stage_ && n_enc) {  // libs/encoder.cpp:491-624 for the whole batch, on worker threads
+          batch_types.resize((size_t)n_enc * mvn);
+          stage_->Run(reinterpret_cast<const Vec2f*>(h_mv), n_enc, first_frame, batch_types.data());
+        }
+        for (uint i = 0; i < n_enc; ++i) {
+          uchar* rec = h_stream + (size_t)i * frame_stream_bytes_;
+          if (stage_) {
+            check(svc_patch_block_types(rec, vidprops_.frame_w, vidprops_.frame_h, cfg_.transform_block_w,
+                                        cfg_.transform_block_h, 3, cfg_.mv_block_w, cfg_.mv_block_h,
+                                        mv_field_w_, batch_types.data() + (size_t)i * mvn));
+          } else if (classify_) {
+            std::fill(block_types.begin(), block_types.end(), 0u);  // BLOCK_TYPE_BACKGROUND, libs/encoder.cpp:549-551
+            classify_(reinterpret_cast<const Vec2f*>(h_mv + (size_t)i * mvn * 2), h_mad + (size_t)i * mvn,
+                      mv_field_w_, mv_field_h_, block_types.data());
+            check(svc_patch_block_types(rec, vidprops_.frame_w, vidprops_.frame_h, cfg_.transform_block_w,
+                                        cfg_.transform_block_h, 3, cfg_.mv_block_w, cfg_.mv_block_h,
+                                        mv_field_w_, block_types.data()));
+          }
+          out_queue_.Push(Bytes(rec, rec + frame_stream_bytes_));
+        }
+      } catch (...) {
+        post_error = std::current_exception();
       }
-      out_queue_.Push(Bytes(rec, rec + frame_stream_bytes_));
-      ++frames_encoded_;
-    }
+    });
   }
+  if (post.joinable()) post.join();
+  if (post_error) std::rethrow_exception(post_error);
   out_queue_.SignalProducerIsDone();  // libs/encoder.cpp:666
 }
 

@@ -152,9 +152,11 @@ class Encoder {
   uint64_t frames_encoded_ = 0;
   // pinned staging owned by the encoder (svc_host_alloc)
   uchar* h_in_ = nullptr;
-  uchar* h_stream_ = nullptr;
-  float* h_mv_ = nullptr;
-  float* h_mad_ = nullptr;
+  // two sets of output staging: a post thread labels, patches and pushes batch k out of one set
+  // while the GPU encodes batch k+1 into the other
+  uchar* h_stream_[2] = {nullptr, nullptr};
+  float* h_mv_[2] = {nullptr, nullptr};
+  float* h_mad_[2] = {nullptr, nullptr};
 };
 
 }  // namespace svc
