@@ -284,73 +284,109 @@ dct8x8_stream_kernel(const DctParams p, const uint32_t nbx, const uint32_t nby_s
   }
 }
 
-// ---- generic separable path -------------------------------------------------
-__constant__ float c_basis_w[32 * 32];
-__constant__ float c_basis_h[32 * 32];
+// ---- generic separable path (any transform block up to 32 x 32) ---------------
+// out = Ch . X . Cw^T per block, C[k][n] = s_k cos(pi (2n+1) k / (2N)) (cv::dct, libs/encoder.cpp:335).
+// One CTA transforms a tile of whole blocks of one channel in shared memory: the tile's pixels are
+// converted to float once, the row pass and the column pass each read a padded basis matrix that
+// travelled as a kernel parameter (no constant-bank upload, no host synchronisation), and the
+// coefficients leave as coalesced row segments.  Sums run over n ascending with fmaf.
+struct DctBasis {
+  float w[32 * 32];  // Cw, tbw x tbw, row k = frequency
+  float h[32 * 32];  // Ch, tbh x tbh
+};
+
+constexpr int kGenTilePx = 1024;  // pixels per tile (upper bound; whole blocks only)
 
 __global__ void __launch_bounds__(256)
-dct_rows_kernel(const uint8_t* __restrict__ bgr, uint32_t w, uint32_t h,
-                uint32_t pw, uint32_t ph, uint32_t tbw, float* __restrict__ tmp,
-                uint64_t total) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const uint32_t x = (uint32_t)(i % pw);
-  const uint32_t y = (uint32_t)((i / pw) % ph);
-  const uint32_t c = (uint32_t)((i / ((uint64_t)pw * ph)) % 3u);
-  const uint64_t f = i / ((uint64_t)pw * ph * 3u);
-  const uint32_t x0 = x / tbw * tbw, k = x - x0;
-  float s = 0.f;
-  if (y < h) {
-    const uint8_t* row = bgr + ((f * h + y) * (uint64_t)w) * 3u + c;
-    for (uint32_t j = 0; j < tbw; ++j)
-      if (x0 + j < w) s = fmaf(c_basis_w[k * tbw + j], (float)__ldg(row + (uint64_t)(x0 + j) * 3u), s);
+dct_generic_planar_kernel(const uint8_t* __restrict__ bgr, uint32_t w, uint32_t h, uint32_t pw, uint32_t ph,
+                          uint32_t tbw, uint32_t tbh, uint32_t tw, uint32_t th, uint32_t tiles_x,
+                          uint32_t tiles_y, float* __restrict__ planes,
+                          const __grid_constant__ DctBasis basis) {
+  __shared__ float sIn[kGenTilePx + 64];   // th rows, pitch tw + 1
+  __shared__ float sTmp[kGenTilePx + 64];
+  __shared__ float sCw[32 * 33], sCh[32 * 33];
+  __shared__ uint8_t sKx[64], sKy[32];     // frequency index of a tile column / row inside its block
+  // blockDim = (64, 4): a thread keeps its column(s), rows advance by 4 -- no division per pixel
+  const uint32_t tx = threadIdx.x, ty = threadIdx.y, tid = ty * 64u + tx;
+  const uint32_t tile = blockIdx.x, c = blockIdx.y, f = blockIdx.z;
+  const uint32_t tile_y = tile / tiles_x;
+  const uint32_t tx0 = (tile - tile_y * tiles_x) * tw, ty0 = tile_y * th;
+  const uint32_t pitch = tw + 1;
+  for (uint32_t i = tid; i < tbw * tbw; i += 256) sCw[(i / tbw) * 33 + i % tbw] = basis.w[i];
+  for (uint32_t i = tid; i < tbh * tbh; i += 256) sCh[(i / tbh) * 33 + i % tbh] = basis.h[i];
+  if (tid < tw) sKx[tid] = (uint8_t)(tid % tbw);
+  if (tid < th) sKy[tid] = (uint8_t)(tid % tbh);
+  const uint8_t* src = bgr + (uint64_t)f * w * h * 3u + c;
+  for (uint32_t y = ty; y < th; y += 4) {
+    const uint32_t gy = ty0 + y;
+    const uint8_t* row = src + (uint64_t)gy * w * 3u;
+    for (uint32_t x = tx; x < tw; x += 64) {
+      const uint32_t gx = tx0 + x;  // zero padding right / below (libs/encoder.cpp:459-461)
+      sIn[y * pitch + x] = (gx < w && gy < h) ? (float)__ldg(row + gx * 3u) : 0.f;
+    }
   }
-  tmp[i] = s;
+  __syncthreads();
+  for (uint32_t x = tx; x < tw; x += 64) {  // row pass
+    const uint32_t k = sKx[x], x0 = x - k;
+    const float* cw = sCw + k * 33;
+    for (uint32_t y = ty; y < th; y += 4) {
+      const float* in = sIn + y * pitch + x0;
+      float acc = 0.f;
+      for (uint32_t j = 0; j < tbw; ++j) acc = fmaf(cw[j], in[j], acc);
+      sTmp[y * pitch + x] = acc;
+    }
+  }
+  __syncthreads();
+  float* dst = planes + ((uint64_t)f * 3u + c) * pw * ph;
+  for (uint32_t y = ty; y < th; y += 4) {  // column pass
+    const uint32_t k = sKy[y], y0 = y - k, gy = ty0 + y;
+    const float* ch = sCh + k * 33;
+    for (uint32_t x = tx; x < tw; x += 64) {
+      const float* in = sTmp + y0 * pitch + x;
+      float acc = 0.f;
+      for (uint32_t j = 0; j < tbh; ++j) acc = fmaf(ch[j], in[j * pitch], acc);
+      const uint32_t gx = tx0 + x;
+      if (gx < pw && gy < ph) dst[(uint64_t)gy * pw + gx] = acc;
+    }
+  }
 }
 
-__global__ void __launch_bounds__(256)
-dct_cols_kernel(const float* __restrict__ tmp, uint32_t pw, uint32_t ph,
-                uint32_t tbh, float* __restrict__ out, uint64_t total) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const uint32_t x = (uint32_t)(i % pw);
-  const uint32_t y = (uint32_t)((i / pw) % ph);
-  const uint64_t plane = i / ((uint64_t)pw * ph);
-  const uint32_t y0 = y / tbh * tbh, k = y - y0;
-  const float* col = tmp + plane * (uint64_t)pw * ph + (uint64_t)y0 * pw + x;
-  float s = 0.f;
-  for (uint32_t j = 0; j < tbh; ++j) s = fmaf(c_basis_h[k * tbh + j], col[(uint64_t)j * pw], s);
-  out[i] = s;
+// SerializeEncodedFrame, libs/encoder.cpp:243-266: one thread per stream word of one frame
+// (blockIdx.y = frame).  Record = block type word + 3 channels of tbw rows x tbh floats -- the
+// reference's swapped loop bounds and unpadded row stride are kept.  Every division is a
+// multiply-high by a host-computed reciprocal (exact: dividend x divisor < 2^32, checked on the host).
+struct GatherDiv {
+  uint32_t rec_words;               // words per record
+  uint32_t nbx, m_nbx;              // records per block row
+  uint32_t area, m_area;            // tbw * tbh
+  uint32_t tbh, m_tbh;
+};
+__device__ __forceinline__ uint32_t div_magic(uint32_t n, uint32_t d, uint32_t m) {
+  return d == 1u ? n : __umulhi(n, m);
 }
 
-// SerializeEncodedFrame, libs/encoder.cpp:243-266, one thread per stream word.
 __global__ void __launch_bounds__(256)
 serialize_gather_kernel(const float* __restrict__ planes, uint64_t plane_elems,
                         const uint32_t* __restrict__ block_types,
-                        uint32_t w, uint32_t h, uint32_t tbw, uint32_t tbh,
+                        uint32_t w, uint32_t tbw, uint32_t tbh,
                         uint32_t mbw, uint32_t mbh, uint32_t mvw, uint32_t mvh,
-                        uint32_t* __restrict__ stream, uint64_t frame_words,
-                        uint64_t total) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const uint64_t f = i / frame_words;
-  const uint64_t wi = i % frame_words;
-  const uint32_t rec_words = 1u + 3u * tbw * tbh;
-  const uint32_t nbx = (w + tbw - 1) / tbw;
-  const uint32_t rec = (uint32_t)(wi / rec_words), k = (uint32_t)(wi % rec_words);
-  const uint32_t tb_x = (rec % nbx) * tbw, tb_y = (rec / nbx) * tbh;
+                        uint32_t* __restrict__ stream, uint32_t frame_words, GatherDiv dv) {
+  const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi >= frame_words) return;
+  const uint32_t f = blockIdx.y;
+  const uint32_t rec = wi / dv.rec_words, k = wi - rec * dv.rec_words;  // (wi * rec_words may exceed 2^32)
+  const uint32_t rec_y = div_magic(rec, dv.nbx, dv.m_nbx);
+  const uint32_t tb_x = (rec - rec_y * dv.nbx) * tbw, tb_y = rec_y * tbh;
   uint32_t out;
   if (k == 0) {
-    out = block_types ? block_types[f * mvw * mvh + (tb_y / mbh) * mvw + tb_x / mbw] : 0u;
+    out = block_types ? block_types[(uint64_t)f * mvw * mvh + (tb_y / mbh) * mvw + tb_x / mbw] : 0u;
   } else {
-    const uint32_t e = k - 1u, c = e / (tbw * tbh), rem = e % (tbw * tbh);
-    const uint32_t row = rem / tbh, j = rem % tbh;  // tbw rows of tbh floats (sic)
-    const uint64_t idx = (uint64_t)(tb_y + row) * w + tb_x + j;  // unpadded stride (sic)
-    out = idx < plane_elems
-              ? __float_as_uint(planes[(f * 3u + c) * plane_elems + idx])
-              : 0u;
+    const uint32_t e = k - 1u, c = div_magic(e, dv.area, dv.m_area), rem = e - c * dv.area;
+    const uint32_t row = div_magic(rem, dv.tbh, dv.m_tbh), j = rem - row * dv.tbh;  // tbw rows of tbh floats (sic)
+    const uint64_t idx = (uint64_t)(tb_y + row) * w + tb_x + j;                     // unpadded stride (sic)
+    out = idx < plane_elems ? __float_as_uint(planes[((uint64_t)f * 3u + c) * plane_elems + idx]) : 0u;
   }
-  stream[i] = out;
+  stream[(uint64_t)f * frame_words + wi] = out;
 }
 
 static void host_basis(uint32_t n, float* out) {
@@ -372,21 +408,20 @@ static cudaError_t planar_into(const DctParams& p, const uint8_t* bgr, uint32_t 
     if (nl) *nl += 1;
     return cudaGetLastError();
   }
-  float hw[32 * 32], hh[32 * 32];
-  host_basis(p.tbw, hw);
-  host_basis(p.tbh, hh);
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_basis_w, hw, sizeof(float) * p.tbw * p.tbw, 0, cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) return e;
-  e = cudaMemcpyToSymbolAsync(c_basis_h, hh, sizeof(float) * p.tbh * p.tbh, 0, cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) return e;
-  // hw/hh live on this stack frame: finish the copies before returning
-  e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return e;
-  const uint64_t total = (uint64_t)nf * 3u * p.pw * p.ph;
-  const uint32_t blocks = (uint32_t)((total + 255) / 256);
-  dct_rows_kernel<<<blocks, 256, 0, st>>>(bgr, p.w, p.h, p.pw, p.ph, p.tbw, tmp, total);
-  dct_cols_kernel<<<blocks, 256, 0, st>>>(tmp, p.pw, p.ph, p.tbh, planes, total);
-  if (nl) *nl += 2;
+  if (p.tbw > 32 || p.tbh > 32 || p.tbw == 0 || p.tbh == 0) return cudaErrorInvalidValue;
+  DctBasis basis;
+  host_basis(p.tbw, basis.w);
+  host_basis(p.tbh, basis.h);
+  // tile = whole blocks, at most 1024 pixels: 16 rows (or one block row) x 64 columns where that fits
+  const uint32_t th = p.tbh * std::max(1u, 16u / p.tbh);
+  const uint32_t tw = p.tbw * std::max(1u, ((uint32_t)kGenTilePx / th) / p.tbw);
+  if (th * (tw + 1) > (uint32_t)kGenTilePx + 64u) return cudaErrorInvalidValue;
+  const uint32_t tiles_x = (p.pw + tw - 1) / tw, tiles_y = (p.ph + th - 1) / th;
+  if (tw > 64u || th > 32u || nf > 65535u || (uint64_t)tiles_x * tiles_y > 0x7fffffffull) return cudaErrorInvalidValue;
+  (void)tmp;
+  dct_generic_planar_kernel<<<dim3(tiles_x * tiles_y, 3, nf), dim3(64, 4), 0, st>>>(
+      bgr, p.w, p.h, p.pw, p.ph, p.tbw, p.tbh, tw, th, tiles_x, tiles_y, planes, basis);
+  if (nl) *nl += 1;
   return cudaGetLastError();
 }
 
@@ -463,13 +498,24 @@ cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* nl) {
         const uint32_t nf = min(p.scratch_frames, p.n_frames - f0);
         e = planar_into(p, p.bgr + f0 * in_frame, nf, sp, tmp, st, nl);
         if (e != cudaSuccess) return e;
-        const uint64_t total = frame_words * nf;
-        serialize_gather_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, st>>>(
+        GatherDiv dv{};
+        dv.rec_words = 1u + 3u * p.tbw * p.tbh;
+        dv.nbx = (p.w + p.tbw - 1) / p.tbw;
+        dv.area = p.tbw * p.tbh;
+        dv.tbh = p.tbh;
+        auto magic = [](uint32_t d) { return d > 1u ? 0xffffffffu / d + 1u : 0u; };  // ceil(2^32 / d)
+        dv.m_nbx = magic(dv.nbx);
+        dv.m_area = magic(dv.area);
+        dv.m_tbh = magic(dv.tbh);
+        // multiply-high by ceil(2^32/d) is the exact quotient while dividend * d < 2^32: records per
+        // frame x records per row, and word-in-record x block area, are far below that
+        if (frame_words >= (1ull << 32) || nf > 65535u) return cudaErrorInvalidValue;
+        serialize_gather_kernel<<<dim3((uint32_t)((frame_words + 255) / 256), nf), 256, 0, st>>>(
             sp, plane_elems,
             p.block_types ? p.block_types + (uint64_t)f0 * p.mv_field_w * p.mv_field_h : nullptr,
-            p.w, p.h, p.tbw, p.tbh, p.mv_block_w, p.mv_block_h, p.mv_field_w, p.mv_field_h,
+            p.w, p.tbw, p.tbh, p.mv_block_w, p.mv_block_h, p.mv_field_w, p.mv_field_h,
             reinterpret_cast<uint32_t*>(p.stream + (uint64_t)f0 * p.frame_stream_bytes),
-            frame_words, total);
+            (uint32_t)frame_words, dv);
         if (nl) *nl += 1;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
