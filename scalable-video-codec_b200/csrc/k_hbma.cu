@@ -171,13 +171,13 @@ hbma_generic_kernel(HbmaParams p) {
 // ---------------------------------------------------------------------------
 __host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-template <int L, int R>
+template <int L, int R, int BB = 16>  // BB: base-level block size (16, or 8 for 8x8 motion blocks)
 struct TileGeom {
   static constexpr int G = 2 * R + 1;   // lanes per motion block
   static constexpr int BPW = 32 / G;    // motion blocks per warp
   static constexpr int TBX = BPW, TBY = 4;
   static constexpr int kThreads = TBY * 32;
-  __host__ __device__ static constexpr int b(int l) { return 16 >> l; }
+  __host__ __device__ static constexpr int b(int l) { return BB >> l; }
   __host__ __device__ static constexpr int d(int l) { return R * ((1 << (L - l)) - 1); }
   // TMA needs the box start 16-byte aligned in the innermost dimension: the box is
   // anchored at floor16(x) and widened by up to 15 bytes.
@@ -259,13 +259,13 @@ struct HbmaTileMaps {
   CUtensorMap a[5];  // anchor-tile boxes, per level
 };
 
-template <int L, int R, int LV>
+template <int L, int R, int BB, int LV>
 __device__ __forceinline__ void tile_level(const uint8_t* smem, const HbmaParams& p, const int g,
                                            const int dxi, const int w, const int tile_bx0,
                                            const int tile_by0, int& mx, int& my, float& cur) {
-  using Gm = TileGeom<L, R>;
+  using Gm = TileGeom<L, R, BB>;
   constexpr int G = Gm::G;
-  constexpr int B = 16 >> LV;
+  constexpr int B = BB >> LV;
   constexpr int D = Gm::d(LV);
   constexpr bool TOP = (LV == L - 1);
   constexpr int PT = Gm::tw(LV), PA = Gm::aw(LV);
@@ -334,10 +334,10 @@ __device__ __forceinline__ void tile_level(const uint8_t* smem, const HbmaParams
   }
 }
 
-template <int L, int R>
-__global__ void __launch_bounds__(TileGeom<L, R>::kThreads)
+template <int L, int R, int BB>
+__global__ void __launch_bounds__(TileGeom<L, R, BB>::kThreads)
 hbma_tile_kernel(const __grid_constant__ HbmaTileMaps maps, const HbmaParams p) {
-  using Gm = TileGeom<L, R>;
+  using Gm = TileGeom<L, R, BB>;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   const int tile_bx0 = blockIdx.x * Gm::TBX, tile_by0 = blockIdx.y * Gm::TBY;
@@ -353,7 +353,7 @@ hbma_tile_kernel(const __grid_constant__ HbmaTileMaps maps, const HbmaParams p) 
                  "r"((uint32_t)Gm::tx_bytes()) : "memory");
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      const int b = 16 >> l;
+      const int b = BB >> l;
       const uint32_t dt = (uint32_t)__cvta_generic_to_shared(smem + Gm::off_t(l));
       const uint32_t da = (uint32_t)__cvta_generic_to_shared(smem + Gm::off_a(l));
       asm volatile(
@@ -382,11 +382,11 @@ hbma_tile_kernel(const __grid_constant__ HbmaTileMaps maps, const HbmaParams p) 
   const bool owner = (lane / Gm::G) < Gm::BPW && dxi == 0;
   int mx = 0, my = 0;
   float cur = FLT_MAX;
-  if constexpr (L >= 5) tile_level<L, R, 4>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
-  if constexpr (L >= 4) tile_level<L, R, 3>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
-  if constexpr (L >= 3) tile_level<L, R, 2>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
-  if constexpr (L >= 2) tile_level<L, R, 1>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
-  tile_level<L, R, 0>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
+  if constexpr (L >= 5) tile_level<L, R, BB, 4>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
+  if constexpr (L >= 4) tile_level<L, R, BB, 3>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
+  if constexpr (L >= 3) tile_level<L, R, BB, 2>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
+  if constexpr (L >= 2) tile_level<L, R, BB, 1>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
+  tile_level<L, R, BB, 0>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
   const uint32_t bx = (uint32_t)(tile_bx0 + g), by = (uint32_t)(tile_by0 + w);
   if (owner && bx < p.mvw && by < p.mvh) {
     const uint64_t o = ((uint64_t)f * p.mvh + by) * p.mvw + bx;
@@ -701,9 +701,10 @@ hbma_window_warp_kernel(const __grid_constant__ HbmaWindowMaps maps, const __gri
 }
 
 // ---- host side: dispatch (tensor-map encoding lives in hbma_dev.cuh) ----------------
-template <int L, int R>
+template <int L, int R, int BB = 16>
 static cudaError_t launch_tile(const HbmaParams& p, cudaStream_t st) {
-  using Gm = TileGeom<L, R>;
+  using Gm = TileGeom<L, R, BB>;
+  static_assert(BB % (1 << (L - 1)) == 0, "top-level block would be empty");
   static_assert(Gm::ok(), "tile geometry does not fit");
   HbmaTileMaps maps;
   const uint32_t n_slots = p.n_frames + 1;
@@ -715,19 +716,28 @@ static cudaError_t launch_tile(const HbmaParams& p, cudaStream_t st) {
                     n_slots, Gm::aw(l), Gm::ah(l)))
       return cudaErrorNotSupported;
   }
-  cudaError_t e = cudaFuncSetAttribute(hbma_tile_kernel<L, R>,
+  cudaError_t e = cudaFuncSetAttribute(hbma_tile_kernel<L, R, BB>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::smem_bytes());
   if (e != cudaSuccess) return e;
   dim3 grid((p.mvw + Gm::TBX - 1) / Gm::TBX, (p.mvh + Gm::TBY - 1) / Gm::TBY, p.n_frames);
-  hbma_tile_kernel<L, R><<<grid, Gm::kThreads, Gm::smem_bytes(), st>>>(maps, p);
+  hbma_tile_kernel<L, R, BB><<<grid, Gm::kThreads, Gm::smem_bytes(), st>>>(maps, p);
   return cudaGetLastError();
 }
 
 // (levels, r) pairs with a tiled instantiation; everything else takes the generic kernel
 static bool try_launch_tile(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
-  if (p.bw != 16 || p.bh != 16 || p.n_frames > 65535) return false;
-  if ((p.mvh + 3) / 4 > 65535) return false;
+  if (p.n_frames > 65535 || (p.mvh + 3) / 4 > 65535) return false;
   const uint32_t L = p.lay.levels, r = p.r;
+  if (p.bw == 8 && p.bh == 8) {  // 8x8 motion blocks: the same kernel, base block 8
+#define SVC_TILE8_CASE(LL, RR) \
+  if (L == LL && r == RR) { *err = launch_tile<LL, RR, 8>(p, st); return true; }
+    SVC_TILE8_CASE(4, 1) SVC_TILE8_CASE(4, 2) SVC_TILE8_CASE(3, 1) SVC_TILE8_CASE(3, 2) SVC_TILE8_CASE(3, 4)
+    SVC_TILE8_CASE(2, 1) SVC_TILE8_CASE(2, 2) SVC_TILE8_CASE(2, 4) SVC_TILE8_CASE(1, 1) SVC_TILE8_CASE(1, 2)
+    SVC_TILE8_CASE(1, 4)
+#undef SVC_TILE8_CASE
+    return false;
+  }
+  if (p.bw != 16 || p.bh != 16) return false;
 #define SVC_TILE_CASE(LL, RR) \
   if (L == LL && r == RR) { *err = launch_tile<LL, RR>(p, st); return true; }
   SVC_TILE_CASE(4, 1) SVC_TILE_CASE(4, 2) SVC_TILE_CASE(4, 3) SVC_TILE_CASE(4, 4)

@@ -109,6 +109,23 @@ def test_hbma_tiled_path_vs_oracle(gpu, oracle, L, R, w, h):
     assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
 
 
+@pytest.mark.parametrize("L,R", [(4, 8), (4, 16), (4, 23), (3, 4), (3, 8), (3, 16), (2, 2), (2, 5), (2, 8), (1, 1),
+                                 (1, 2), (1, 4)])
+@pytest.mark.parametrize("w,h", [(328, 200), (88, 40), (8, 64)])
+def test_hbma_tiled_path_8x8_blocks(gpu, oracle, L, R, w, h):
+    """8x8 motion blocks on the TMA-staged tiled kernel with base block 8: the top
+    level of L = 4 compares single pixels; partial tiles, one-block-wide frames, clamping."""
+    pw, ph = gpu.padded_dim(w, 8, L), gpu.padded_dim(h, 8, L)
+    seq = SyntheticSequence(w, h, 2, seed=L * 11 + R, n_rects=2)
+    p0, p1 = oracle.y_pyramid(seq.frame(0), pw, ph, L), oracle.y_pyramid(seq.frame(1), pw, ph, L)
+    mv, mad = gpu.EstimateMotionHierarchical(p0, p1, L, pw, ph, R, 8, 8)
+    emv, emad = oracle.hbma(p0, p1, R, 8, 8)
+    assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+    z = [np.zeros_like(a) for a in p0]  # flat frames: ties everywhere, zero-vector rule
+    mv, mad = gpu.EstimateMotionHierarchical(z, z, L, pw, ph, R, 8, 8)
+    assert not mv.any() and not mad.any()
+
+
 @pytest.mark.parametrize("L,R", [(4, 64), (4, 100), (3, 32), (3, 60), (2, 32), (2, 10), (1, 3), (1, 8),
                                  (1, 16), (1, 40), (5, 80), (5, 128)])
 @pytest.mark.parametrize("w,h", [(176, 112), (64, 48)])
