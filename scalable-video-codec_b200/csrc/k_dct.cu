@@ -351,6 +351,58 @@ dct_generic_planar_kernel(const uint8_t* __restrict__ bgr, uint32_t w, uint32_t 
   }
 }
 
+// Square power-of-two blocks (2, 4, 16, 32): the same two passes with the loops unrolled.  A thread
+// takes one block row (then one block column): TB values into registers, TB x TB FMAs whose basis
+// factors are constant-bank operands (the basis is a kernel parameter, the indices are compile
+// time), so the FMA pipe is the only busy unit.  Tile = 64 x 64 pixels of one channel.
+template <int TB>
+__global__ void __launch_bounds__(256)
+dct_square_planar_kernel(const uint8_t* __restrict__ bgr, uint32_t w, uint32_t h, uint32_t pw, uint32_t ph,
+                         uint32_t tiles_x, float* __restrict__ planes, const __grid_constant__ DctBasis basis) {
+  constexpr int T = 64, PITCH = T + 1, NBT = T / TB;  // blocks per tile row / column
+  __shared__ float sA[T * PITCH], sB[T * PITCH];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t tile = blockIdx.x, c = blockIdx.y, f = blockIdx.z;
+  const uint32_t tile_y = tile / tiles_x;
+  const uint32_t tx0 = (tile - tile_y * tiles_x) * T, ty0 = tile_y * T;
+  const uint8_t* src = bgr + (uint64_t)f * w * h * 3u + c;
+  for (uint32_t i = tid; i < T * T; i += 256) {
+    const uint32_t y = i >> 6, x = i & 63u, gx = tx0 + x, gy = ty0 + y;
+    sA[y * PITCH + x] = (gx < w && gy < h) ? (float)__ldg(src + ((uint64_t)gy * w + gx) * 3u) : 0.f;
+  }
+  __syncthreads();
+  for (uint32_t it = tid; it < T * NBT; it += 256) {  // row pass: (row y, block bx)
+    const uint32_t y = it / NBT, bx = it - y * NBT;
+    float v[TB];
+#pragma unroll
+    for (int j = 0; j < TB; ++j) v[j] = sA[y * PITCH + bx * TB + j];
+#pragma unroll
+    for (int k = 0; k < TB; ++k) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < TB; ++j) acc = fmaf(basis.w[k * TB + j], v[j], acc);
+      sB[y * PITCH + bx * TB + k] = acc;
+    }
+  }
+  __syncthreads();
+  float* dst = planes + ((uint64_t)f * 3u + c) * pw * ph;
+  for (uint32_t it = tid; it < T * NBT; it += 256) {  // column pass: (block by, column x)
+    const uint32_t by = it >> 6, x = it & 63u;
+    float v[TB];
+#pragma unroll
+    for (int j = 0; j < TB; ++j) v[j] = sB[(by * TB + j) * PITCH + x];
+    const uint32_t gx = tx0 + x;
+#pragma unroll
+    for (int k = 0; k < TB; ++k) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < TB; ++j) acc = fmaf(basis.h[k * TB + j], v[j], acc);
+      const uint32_t gy = ty0 + by * TB + k;
+      if (gx < pw && gy < ph) dst[(uint64_t)gy * pw + gx] = acc;
+    }
+  }
+}
+
 // SerializeEncodedFrame, libs/encoder.cpp:243-266: one thread per stream word of one frame
 // (blockIdx.y = frame).  Record = block type word + 3 channels of tbw rows x tbh floats -- the
 // reference's swapped loop bounds and unpadded row stride are kept.  Every division is a
@@ -412,6 +464,18 @@ static cudaError_t planar_into(const DctParams& p, const uint8_t* bgr, uint32_t 
   DctBasis basis;
   host_basis(p.tbw, basis.w);
   host_basis(p.tbh, basis.h);
+  if (p.tbw == p.tbh && (p.tbw == 2 || p.tbw == 4 || p.tbw == 16 || p.tbw == 32) && nf <= 65535u) {
+    const uint32_t tiles_x = (p.pw + 63u) / 64u, tiles_y = (p.ph + 63u) / 64u;
+    const dim3 grid(tiles_x * tiles_y, 3, nf);
+    switch (p.tbw) {
+      case 2: dct_square_planar_kernel<2><<<grid, 256, 0, st>>>(bgr, p.w, p.h, p.pw, p.ph, tiles_x, planes, basis); break;
+      case 4: dct_square_planar_kernel<4><<<grid, 256, 0, st>>>(bgr, p.w, p.h, p.pw, p.ph, tiles_x, planes, basis); break;
+      case 16: dct_square_planar_kernel<16><<<grid, 256, 0, st>>>(bgr, p.w, p.h, p.pw, p.ph, tiles_x, planes, basis); break;
+      default: dct_square_planar_kernel<32><<<grid, 256, 0, st>>>(bgr, p.w, p.h, p.pw, p.ph, tiles_x, planes, basis); break;
+    }
+    if (nl) *nl += 1;
+    return cudaGetLastError();
+  }
   // tile = whole blocks, at most 1024 pixels: 16 rows (or one block row) x 64 columns where that fits
   const uint32_t th = p.tbh * std::max(1u, 16u / p.tbh);
   const uint32_t tw = p.tbw * std::max(1u, ((uint32_t)kGenTilePx / th) / p.tbw);
