@@ -50,6 +50,7 @@ inline bool encode_box(CUtensorMap* m, const uint8_t* base, uint32_t w, uint32_t
 // large-range 16x16 search with pooled work items and pre-shifted window copies (k_hbma_pool.cu);
 // returns false when the configuration is outside its limits (the caller picks another kernel)
 struct HbmaParams;
-bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err);
+// (*extra_launches += launches beyond the first, for the level-synchronous path)
+bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int* extra_launches);
 
 }  // namespace svc

@@ -820,7 +820,7 @@ cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches) {
   static const bool env_generic = getenv("SVC_HBMA_FORCE_GENERIC") != nullptr;  // test hook
   if (!p.force_generic && !env_generic) {
     cudaError_t e = cudaSuccess;
-    if (try_launch_tile(p, st, &e) || try_launch_pool(p, st, &e) || try_launch_window(p, st, &e)) {
+    if (try_launch_tile(p, st, &e) || try_launch_pool(p, st, &e, n_launches) || try_launch_window(p, st, &e)) {
       if (n_launches) *n_launches += 1;
       return e;
     }

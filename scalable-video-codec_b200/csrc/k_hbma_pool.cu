@@ -61,21 +61,22 @@ struct PoolGeom {
 // Top level only (L = 1, i.e. plain EBMA): the window position does not depend on data, so the NBX
 // horizontally adjacent blocks of a CTA share ONE window (one TMA load, one copy build): it is
 // 16 NBX + 2r wide instead of NBX (16 + 2r).
-template <int RC, int NBX, int NDY>
+template <int RC, int NBX, int NDY, int B = 16>
 struct TileGeomE {
-  static constexpr int PT = (16 * NBX + 2 * RC + 15 + 15) & ~15;
-  static constexpr int ROWS = 16 + 2 * RC + NDY;
+  static_assert((B * NBX) % 16 == 0, "the anchor tile is a TMA box: its rows must be multiples of 16 bytes");
+  static constexpr int PT = (B * NBX + 2 * RC + 15 + 15) & ~15;
+  static constexpr int ROWS = B + 2 * RC + NDY;
   static constexpr int CS = ((PT * ROWS + 16 + 127) & ~127) + 32;
-  static constexpr int PA = 16 * NBX;
-  static constexpr int OFF_A = 4 * CS;                       // anchor tile: 16 rows x PA
+  static constexpr int PA = B * NBX;
+  static constexpr int OFF_A = 4 * CS;                       // anchor tile: B rows x PA
   static constexpr int NCH = (2 * RC + 1 + NDY - 1) / NDY;
   static constexpr int MAXWR = (NBX * (2 * RC + 1) * NCH + 31) / 32;
   static constexpr int EDGE = 2 * (MAXWR + NBX * NCH) * NDY * 2;
-  static constexpr int OFF_EDGE = (OFF_A + 16 * PA + 127) & ~127;
+  static constexpr int OFF_EDGE = (OFF_A + B * PA + 127) & ~127;
   static constexpr int SMEM = OFF_EDGE + EDGE;
   static constexpr int kNB = NBX, kNDY = NDY;
   __device__ static const uint8_t* window(const uint8_t* smem, int, int ph) { return smem + ph * CS; }
-  __device__ static const uint8_t* anchor(const uint8_t* smem, int j) { return smem + OFF_A + j * 16; }
+  __device__ static const uint8_t* anchor(const uint8_t* smem, int j) { return smem + OFF_A + j * B; }
 };
 
 struct PoolLv {  // one motion block at the current level
@@ -497,10 +498,13 @@ struct EbmaMaps {
   CUtensorMap a;  // anchor tile box: 16 NBX x 16
 };
 
-template <int RC, int NBX, int NDY, int THREADS, int MINB>
+// B = block size at the searched level `lvl` (16 >> lvl): 16 / level 0 for L = 1; the top level of a
+// deeper pyramid otherwise, whose vector and MAD it leaves in p.mv / p.mad for hbma_refine_kernel.
+template <int RC, int NBX, int NDY, int THREADS, int MINB, int B = 16>
 __global__ void __launch_bounds__(THREADS, MINB)
-hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ HbmaParams p) {
-  using G = TileGeomE<RC, NBX, NDY>;
+hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ HbmaParams p,
+                      const int lvl) {
+  using G = TileGeomE<RC, NBX, NDY, B>;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ PoolLv sLv[NBX];
@@ -515,11 +519,11 @@ hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_consta
   const uint32_t tiles_per_row = (p.mvw + NBX - 1) / NBX, tiles_per_frame = tiles_per_row * p.mvh;
   const uint32_t f = blockIdx.x / tiles_per_frame, ti = blockIdx.x - f * tiles_per_frame;
   const int by = (int)(ti / tiles_per_row), bx0 = (int)(ti - (uint32_t)by * tiles_per_row) * NBX;
-  const int fw = (int)p.lay.w[0], fh = (int)p.lay.h[0];
-  const int ay = by * 16;
-  const int y0 = max(0, ay - r), y1 = min(fh - 16 + 1, ay + r + 1);
-  const int wx = max(0, bx0 * 16 - r) & ~15;  // 16-byte aligned origin of the shared window
-  const int box_h = 16 + 2 * r;
+  const int fw = (int)p.lay.w[lvl], fh = (int)p.lay.h[lvl];
+  const int ay = by * B;
+  const int y0 = max(0, ay - r), y1 = min(fh - B + 1, ay + r + 1);
+  const int wx = max(0, bx0 * B - r) & ~15;  // 16-byte aligned origin of the shared window
+  const int box_h = B + 2 * r;
   const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
 
   // thread j < NBX owns block bx0 + j
@@ -528,9 +532,9 @@ hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_consta
   if (tid < NBX) {
     PoolLv v{};
     if (own) {
-      ax = (bx0 + tid) * 16;
+      ax = (bx0 + tid) * B;
       x0 = max(0, ax - r);
-      const int x1 = min(fw - 16 + 1, ax + r + 1);
+      const int x1 = min(fw - B + 1, ax + r + 1);
       ncx = x1 - x0;
       const int ncy = y1 - y0;
       const int nch = (ncy + NDY - 1) / NDY;
@@ -545,7 +549,7 @@ hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_consta
       v.scan_dx0 = 0;
       if (p.counters) {
         atomicAdd(p.counters, (unsigned long long)(ncx * ncy));
-        atomicAdd(p.counters + 1, (unsigned long long)(ncx * ncy) * 256ull);
+        atomicAdd(p.counters + 1, (unsigned long long)(ncx * ncy) * (unsigned long long)(B * B));
       }
     }
     sLv[tid] = v;
@@ -556,14 +560,14 @@ hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_consta
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
-                 "r"((uint32_t)(G::PT * box_h + 16 * G::PA)) : "memory");
+                 "r"((uint32_t)(G::PT * box_h + B * G::PA)) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(&maps.t), "r"(wx), "r"(y0), "r"((int)f),
         "r"(bar_addr) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"((uint32_t)__cvta_generic_to_shared(smem + G::OFF_A)), "l"(&maps.a), "r"(bx0 * 16), "r"(ay),
+        ::"r"((uint32_t)__cvta_generic_to_shared(smem + G::OFF_A)), "l"(&maps.a), "r"(bx0 * B), "r"(ay),
         "r"((int)f + 1), "r"(bar_addr) : "memory");
   }
   __syncthreads();  // barrier initialised before anyone polls it; sLv / sBest / sViol published
@@ -583,7 +587,7 @@ hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_consta
   beg[0] = 0;
 #pragma unroll
   for (int j = 0; j < NBX; ++j) beg[j + 1] = beg[j] + sLv[j].n_items;
-  pool_level<16, G, THREADS>(smem, sLv, beg, true, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC);
+  pool_level<B, G, THREADS>(smem, sLv, beg, true, sBest, sViol, sTailW, sHeadW, sTailC, sHeadC);
   __syncthreads();
   {  // scan-order neighbours that were not in adjacent lanes (as in hbma_pool_kernel)
     const int total = beg[NBX];
@@ -615,7 +619,7 @@ hbma_ebma_tile_kernel(const __grid_constant__ EbmaMaps maps, const __grid_consta
     const uint64_t o = ((uint64_t)f * p.mvh + (uint32_t)by) * p.mvw + (uint32_t)(bx0 + tid);
     if (p.mv) p.mv[o] = any_viol ? make_float2((float)(x0 + idx % ncx - ax), (float)(y0 + idx / ncx - ay))
                                  : make_float2(0.f, 0.f);
-    if (p.mad) p.mad[o] = (float)(best >> 16) * (1.0f / 256.0f);
+    if (p.mad) p.mad[o] = (float)(best >> 16) * (1.0f / (float)(B * B));
   }
 }
 
@@ -767,6 +771,235 @@ hbma_ebma_stripe_kernel(const __grid_constant__ EbmaMaps maps, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Level-synchronous path for pyramids (2 <= L <= 4, r <= 32): one launch per level.  The top
+// level runs on hbma_ebma_tile_kernel (shared windows); every refinement level on the kernel
+// below, which is hbma_pool_kernel reduced to ONE level with a compile-time block size: the
+// anchor block takes B*B/4 registers instead of 64, no level loop, no top-level code, so more
+// CTAs share an SM.  The vector and MAD of the coarser level travel through p.mv / p.mad (the
+// output arrays), exactly the values the reference carries between its RefineHierMotionEst calls
+// (libs/motion.cpp:451-464).
+// ---------------------------------------------------------------------------------------
+template <int RC, int NB, int NDY, int B>
+struct RefineGeom {
+  static constexpr int PT = (B + 2 * RC + 15 + 15) & ~15;
+  static constexpr int ROWS = B + 2 * RC + NDY;
+  static constexpr int CS = ((PT * ROWS + 16 + 127) & ~127) + 32;
+  static constexpr int BLK = 4 * CS + ((16 * B + 127) & ~127);  // 4 copies + anchor block (pitch 16)
+  static constexpr int SMEM = NB * BLK;
+  static constexpr int PA = 16, NCH = 1;
+  static constexpr int kNB = NB, kNDY = NDY;
+  __device__ static const uint8_t* window(const uint8_t* smem, int j, int ph) { return smem + j * BLK + ph * CS; }
+  __device__ static const uint8_t* anchor(const uint8_t* smem, int j) { return smem + j * BLK + 4 * CS; }
+};
+
+template <int RC, int NB, int NDY, int THREADS, int MINB, int B>
+__global__ void __launch_bounds__(THREADS, MINB)
+hbma_refine_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ HbmaParams p, const int lvl) {
+  using G = RefineGeom<RC, NB, NDY, B>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ PoolLv sLv[NB];
+  __shared__ uint32_t sBest[NB];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t per_frame = p.mvw * p.mvh;
+  const uint32_t n_blocks = per_frame * p.n_frames;  // < 2^31 (checked on the host)
+  const int r = (int)p.r;
+  const int box_h = B + 2 * r;
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_addr), "r"(NB));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int mx = 0, my = 0, x0 = 0, y0 = 0, ncx = 1, ax = 0, ay = 0;
+  float cur = 0.f;
+  uint32_t gb = 0;
+  bool own = false;
+  if (tid < NB) {
+    gb = blockIdx.x * NB + tid;
+    own = gb < n_blocks;
+    PoolLv v{};
+    if (own) {
+      const uint32_t f = gb / per_frame, bi = gb - f * per_frame;
+      const int bx = (int)(bi % p.mvw), by = (int)(bi / p.mvw);
+      const float2 m = p.mv[gb];  // integer valued (libs/motion.cpp:326-327, 403-404)
+      cur = p.mad[gb];
+      mx = 2 * (int)m.x;          // motion_field *= 2 between levels (libs/motion.cpp:459)
+      my = 2 * (int)m.y;
+      const int fw = (int)p.lay.w[lvl], fh = (int)p.lay.h[lvl];
+      ax = bx * B;
+      ay = by * B;
+      const int cx = ax + mx, cy = ay + my;
+      x0 = max(0, cx - r);
+      y0 = max(0, cy - r);
+      const int x1 = min(fw - B + 1, cx + r + 1), y1 = min(fh - B + 1, cy + r + 1);
+      ncx = x1 - x0;
+      const int ncy = y1 - y0;
+      const int nch = (ncy + NDY - 1) / NDY;
+      v.x0 = x0; v.y0 = y0; v.ncx = ncx; v.ncy = ncy;
+      v.nch = nch;
+      v.csz = (ncy + nch - 1) / nch;
+      v.sxb = x0 & 15;
+      v.aoff = ax & 15;
+      v.magic = ncx > 1 ? 0xffffffffu / (uint32_t)ncx + 1u : 0u;
+      v.n_items = ncx * nch;
+      v.scan_ncx = ncx;
+      v.scan_dx0 = 0;
+      if (p.counters) {
+        atomicAdd(p.counters, (unsigned long long)(ncx * ncy));
+        atomicAdd(p.counters + 1, (unsigned long long)(ncx * ncy) * (unsigned long long)(B * B));
+      }
+      sLv[tid] = v;
+      sBest[tid] = 0xffffffffu;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                   "r"((uint32_t)(G::PT * box_h + 16 * B)) : "memory");
+      uint8_t* blk = smem + tid * G::BLK;
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(blk)), "l"(&maps.t), "r"(x0 & ~15), "r"(y0), "r"((int)f),
+          "r"(bar_addr) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(blk + 4 * G::CS)), "l"(&maps.a), "r"(ax & ~15), "r"(ay),
+          "r"((int)f + 1), "r"(bar_addr) : "memory");
+    } else {
+      sLv[tid] = v;
+      sBest[tid] = 0xffffffffu;
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+    }
+  }
+  {  // windows landed; sLv / sBest published (arrive = release, wait = acquire)
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar_addr), "r"(0u) : "memory");
+    }
+  }
+  {  // shifted copies of the NB windows, as one flat list of 16-byte vectors (see hbma_pool_kernel)
+    const int nvec = (G::PT / 16) * box_h, total = NB * nvec;
+    const uint32_t vmagic = 0xffffffffu / (uint32_t)nvec + 1u;
+    for (int vb = tid - lane; vb < total; vb += 4 * THREADS) {
+      const int v0 = vb + lane;
+      uint4 v[4];
+      uint32_t nx[4];
+      uint8_t* dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int vi = min(v0 + u * THREADS, total - 1);
+        const int j = NB > 1 ? (int)__umulhi((uint32_t)vi, vmagic) : 0;
+        uint8_t* q = smem + j * G::BLK + (vi - j * nvec) * 16;
+        v[u] = *reinterpret_cast<const uint4*>(q);
+        dst[u] = q;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        nx[u] = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+        if (lane == 31) nx[u] = *reinterpret_cast<const uint32_t*>(dst[u] + 16);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (v0 + u * THREADS < total) {
+#pragma unroll
+          for (int sft = 1; sft < 4; ++sft) {
+            uint4 o;
+            o.x = __funnelshift_r(v[u].x, v[u].y, 8 * sft);
+            o.y = __funnelshift_r(v[u].y, v[u].z, 8 * sft);
+            o.z = __funnelshift_r(v[u].z, v[u].w, 8 * sft);
+            o.w = __funnelshift_r(v[u].w, nx[u], 8 * sft);
+            *reinterpret_cast<uint4*>(dst[u] + sft * G::CS) = o;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  int beg[NB + 1];
+  beg[0] = 0;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) beg[j + 1] = beg[j] + sLv[j].n_items;
+  pool_level<B, G, THREADS>(smem, sLv, beg, false, sBest, nullptr, nullptr, nullptr, nullptr, nullptr);
+  __syncthreads();
+  if (own) {  // strict "<" against the MAD carried from the coarser level (libs/motion.cpp:401-405)
+    const uint32_t best = sBest[tid];
+    const float m = (float)(best >> 16) * (1.0f / (float)(B * B));
+    if (best != 0xffffffffu && m < cur) {
+      const int idx = (int)(best & 0xffffu);
+      cur = m;
+      mx = x0 + idx % ncx - ax;
+      my = y0 + idx / ncx - ay;
+    }
+    p.mv[gb] = make_float2((float)mx, (float)my);
+    p.mad[gb] = cur;
+  }
+}
+
+template <int RC, int NBX, int NDY, int THREADS, int MINB, int B>
+static cudaError_t launch_top_tile(const HbmaParams& p, uint32_t lvl, cudaStream_t st) {
+  using G = TileGeomE<RC, NBX, NDY, B>;
+  static_assert(G::SMEM <= 227 * 1024 && G::PT <= 256 && G::PA <= 256, "tile geometry does not fit");
+  EbmaMaps maps;
+  const uint32_t n_slots = p.n_frames + 1;
+  const uint8_t* base = p.pyr + p.lay.off[lvl];
+  if (!encode_box(&maps.t, base, p.lay.w[lvl], p.lay.h[lvl], p.lay.pitch[lvl], p.lay.slot_bytes, n_slots, G::PT,
+                  B + 2 * p.r) ||
+      !encode_box(&maps.a, base, p.lay.w[lvl], p.lay.h[lvl], p.lay.pitch[lvl], p.lay.slot_bytes, n_slots, G::PA, B))
+    return cudaErrorNotSupported;
+  auto kern = hbma_ebma_tile_kernel<RC, NBX, NDY, THREADS, MINB, B>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+  if (e != cudaSuccess) return e;
+  const uint64_t tiles = (uint64_t)((p.mvw + NBX - 1) / NBX) * p.mvh * p.n_frames;
+  kern<<<(uint32_t)tiles, THREADS, G::SMEM, st>>>(maps, p, (int)lvl);
+  return cudaGetLastError();
+}
+
+template <int RC, int NB, int NDY, int THREADS, int MINB, int B>
+static cudaError_t launch_refine(const HbmaParams& p, uint32_t lvl, cudaStream_t st) {
+  using G = RefineGeom<RC, NB, NDY, B>;
+  static_assert(G::SMEM <= 227 * 1024 && G::PT <= 256, "refine geometry does not fit");
+  EbmaMaps maps;
+  const uint32_t n_slots = p.n_frames + 1;
+  const uint8_t* base = p.pyr + p.lay.off[lvl];
+  if (!encode_box(&maps.t, base, p.lay.w[lvl], p.lay.h[lvl], p.lay.pitch[lvl], p.lay.slot_bytes, n_slots, G::PT,
+                  B + 2 * p.r) ||
+      !encode_box(&maps.a, base, p.lay.w[lvl], p.lay.h[lvl], p.lay.pitch[lvl], p.lay.slot_bytes, n_slots, 16, B))
+    return cudaErrorNotSupported;
+  auto kern = hbma_refine_kernel<RC, NB, NDY, THREADS, MINB, B>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+  if (e != cudaSuccess) return e;
+  const uint64_t n_blocks = (uint64_t)p.mvw * p.mvh * p.n_frames;
+  kern<<<(uint32_t)((n_blocks + NB - 1) / NB), THREADS, G::SMEM, st>>>(maps, p, (int)lvl);
+  return cudaGetLastError();
+}
+
+// top level with block size BT = 16 >> (L-1), then the refinement levels down to 16x16
+template <int RC, int NDY, int NB_REF, int THR_REF, int MINB_REF>
+static cudaError_t launch_levels(const HbmaParams& p, cudaStream_t st, int* n_launches) {
+  const uint32_t L = p.lay.levels;
+  constexpr int PAW = RC <= 16 ? 80 : 48;  // anchor tile width of the top-level tiles (bytes)
+  cudaError_t e;
+  switch (L) {
+    case 2: e = launch_top_tile<RC, PAW / 8, NDY, 256, 3, 8>(p, 1, st); break;
+    case 3: e = launch_top_tile<RC, PAW / 4, NDY, 256, 3, 4>(p, 2, st); break;
+    default: e = launch_top_tile<RC, PAW / 2, NDY, 256, 3, 2>(p, 3, st); break;
+  }
+  if (e != cudaSuccess) return e;
+  if (L >= 4) {
+    e = launch_refine<RC, NB_REF, NDY, THR_REF, 4, 4>(p, 2, st);
+    if (e != cudaSuccess) return e;
+  }
+  if (L >= 3) {
+    e = launch_refine<RC, NB_REF, NDY, THR_REF, 4, 8>(p, 1, st);
+    if (e != cudaSuccess) return e;
+  }
+  e = launch_refine<RC, NB_REF, NDY, THR_REF, MINB_REF, 16>(p, 0, st);
+  if (n_launches) *n_launches += (int)L - 1;  // the caller counts one
+  return e;
+}
+
 template <int RC, int CW, int NDY, int THREADS, int MINB>
 static cudaError_t launch_ebma_stripe(const HbmaParams& p, cudaStream_t st) {
   using G = StripeGeomE<RC, CW, NDY>;
@@ -797,11 +1030,11 @@ static cudaError_t launch_ebma_tile(const HbmaParams& p, cudaStream_t st) {
                   16 + 2 * p.r) ||
       !encode_box(&maps.a, base, p.lay.w[0], p.lay.h[0], p.lay.pitch[0], p.lay.slot_bytes, n_slots, G::PA, 16))
     return cudaErrorNotSupported;
-  auto kern = hbma_ebma_tile_kernel<RC, NBX, NDY, THREADS, MINB>;
+  auto kern = hbma_ebma_tile_kernel<RC, NBX, NDY, THREADS, MINB, 16>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
   if (e != cudaSuccess) return e;
   const uint64_t tiles = (uint64_t)((p.mvw + NBX - 1) / NBX) * p.mvh * p.n_frames;
-  kern<<<(uint32_t)tiles, THREADS, G::SMEM, st>>>(maps, p);
+  kern<<<(uint32_t)tiles, THREADS, G::SMEM, st>>>(maps, p, 0);
   return cudaGetLastError();
 }
 
@@ -829,11 +1062,29 @@ static cudaError_t launch_pool(const HbmaParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
+bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int* extra_launches) {
   static const bool off = getenv("SVC_HBMA_NO_POOL") != nullptr;  // experiment hook
   const uint32_t L = p.lay.levels, r = p.r;
   if (off || p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > (L == 1 ? 112u : 64u)) return false;
   if ((uint64_t)p.mvw * p.mvh * p.n_frames > 0x7fffffffull) return false;
+  static const bool no_levels = getenv("SVC_HBMA_NO_LEVELS") != nullptr;  // experiment hook
+  if (L >= 2 && L <= 4 && r <= 32 && p.mv && p.mad && !no_levels && getenv("SVC_HBMA_FORCE_POOL") == nullptr) {
+    // one launch per level; <range class, candidate rows per item, blocks per CTA and CTAs per SM of
+    // the 16x16 refinement level>
+    static const char* env_lv = getenv("SVC_HBMA_POOL_VARIANT");  // tuning hook
+    const int lv = env_lv ? atoi(env_lv) : 0;
+    if (r <= 8) {
+      if (lv == 1) *err = launch_levels<8, 9, 7, 128, 4>(p, st, extra_launches);
+      else *err = launch_levels<8, 17, 7, 128, 3>(p, st, extra_launches);
+    } else if (r <= 16) {
+      if (lv == 1) *err = launch_levels<16, 11, 3, 160, 4>(p, st, extra_launches);
+      else *err = launch_levels<16, 11, 3, 128, 4>(p, st, extra_launches);
+    } else {
+      if (lv == 1) *err = launch_levels<32, 13, 1, 128, 4>(p, st, extra_launches);
+      else *err = launch_levels<32, 13, 2, 128, 3>(p, st, extra_launches);
+    }
+    return true;
+  }
   // Deep pyramids with a small top-level range are dominated by the per-level fixed costs (TMA
   // round trip, copy build, barriers) of the small coarse levels: the warp-per-block window
   // kernel of k_hbma.cu, which has no block-wide barrier, measures a little faster there.
@@ -842,7 +1093,7 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
   static const char* env_v = getenv("SVC_HBMA_POOL_VARIANT");  // tuning hook
   const int variant = env_v ? atoi(env_v) : 0;
   // <range class, blocks per CTA, candidate rows per item, threads, CTAs per SM>: measured best of
-  // several shapes per class on B200 (profiles/r01_sweep_hbma_v9.md)
+  // several shapes per class on B200 (profiles/r01_sweep_hbma_v10.md)
   static const bool no_tile = getenv("SVC_HBMA_NO_EBMA_TILE") != nullptr;  // experiment hook
   if (L == 1 && r > 32 && !no_tile) {
     // <range class, stripe width in candidate columns, candidate rows per item, threads, CTAs per SM>

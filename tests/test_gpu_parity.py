@@ -157,6 +157,28 @@ def test_hbma_pooled_window_path_vs_oracle(gpu, oracle, L, R, w, h, monkeypatch)
     assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
 
 
+@pytest.mark.parametrize("L,R", [(2, 10), (2, 16), (2, 27), (2, 32), (2, 50), (2, 64), (3, 20), (3, 32), (3, 45),
+                                 (3, 64), (3, 100), (3, 128), (4, 40), (4, 64), (4, 100), (4, 128), (4, 200), (4, 256)])
+@pytest.mark.parametrize("w,h", [(416, 240), (48, 176)])
+def test_hbma_level_synchronous_path_vs_oracle(gpu, oracle, L, R, w, h):
+    """2..4 levels, top-level range 5..32: one launch per level (shared-window tile kernel at the top
+    level, single-level refinement kernels below), the coarser level's vector and MAD carried through
+    the output arrays -- partial tiles, frames narrower than a window, flat-patch ties, the
+    zero-vector rule of the top level and the strict '<' of the refinement levels."""
+    pw, ph = gpu.padded_dim(w, 16, L), gpu.padded_dim(h, 16, L)
+    seq = SyntheticSequence(w, h, 2, seed=L * 19 + R)
+    p0, p1 = oracle.y_pyramid(seq.frame(0), pw, ph, L), oracle.y_pyramid(seq.frame(1), pw, ph, L)
+    mv, mad = gpu.EstimateMotionHierarchical(p0, p1, L, pw, ph, R, 16, 16)
+    emv, emad = oracle.hbma(p0, p1, R)
+    assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+    z = [np.zeros_like(a) for a in p0]
+    f = [np.full_like(a, 255) for a in p0]
+    for t, a in ((z, z), (z, f)):
+        mv, mad = gpu.EstimateMotionHierarchical(t, a, L, pw, ph, R, 16, 16)
+        emv, emad = oracle.hbma(t, a, R)
+        assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+
+
 @pytest.mark.parametrize("R,L", [(8, 1), (16, 1), (32, 1), (40, 1), (64, 1), (100, 1), (64, 2)])
 def test_hbma_pooled_window_monotone_sequences(gpu, oracle, R, L):
     """Top-level zero-vector rule (libs/motion.cpp:333-337) on the pooled kernel: horizontal /
