@@ -1,10 +1,11 @@
 // k_hbma_pool.cu -- K2, large search ranges (16x16 blocks, top-level range r >= 5): the
-// SAD-bound regime of the range / level sweep (BASELINE config 3).  Three kernels:
+// SAD-bound regime of the range / level sweep (BASELINE config 3).  Four kernels:
 //   hbma_pool_kernel         any pyramid depth, r = 5..64: per-block windows, pooled work items
+//   hbma_refine_kernel       one refinement level of a pyramid (one launch per level, r <= 32)
 //   hbma_ebma_tile_kernel    L = 1, r <= 32: one shared window per tile of adjacent blocks
 //   hbma_ebma_stripe_kernel  L = 1, r = 33..112: one block per CTA, window in column stripes
 // (L = 1 is EstimateMotionExhaustiveSearch, libs/motion.cpp:268-340; the window position is then
-// not data dependent).  All three share the work-item code (pool_level / sad_column_pre).
+// not data dependent; the tile kernel also searches the top level of deeper pyramids).  All share the work-item code (pool_level / sad_column_pre).
 //
 // Same arithmetic and scan-order rules as k_hbma.cu (reference libs/motion.cpp:268-465,
 // 691-749); this file only changes how the work is laid out on the SM, to keep the
@@ -772,7 +773,7 @@ hbma_ebma_stripe_kernel(const __grid_constant__ EbmaMaps maps, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------
-// Level-synchronous path for pyramids (2 <= L <= 4, r <= 32): one launch per level.  The top
+// Level-synchronous path for pyramids (2 <= L <= 5, r <= 32): one launch per level.  The top
 // level runs on hbma_ebma_tile_kernel (shared windows); every refinement level on the kernel
 // below, which is hbma_pool_kernel reduced to ONE level with a compile-time block size: the
 // anchor block takes B*B/4 registers instead of 64, no level loop, no top-level code, so more
@@ -984,9 +985,14 @@ static cudaError_t launch_levels(const HbmaParams& p, cudaStream_t st, int* n_la
   switch (L) {
     case 2: e = launch_top_tile<RC, PAW / 8, NDY, 256, 3, 8>(p, 1, st); break;
     case 3: e = launch_top_tile<RC, PAW / 4, NDY, 256, 3, 4>(p, 2, st); break;
-    default: e = launch_top_tile<RC, PAW / 2, NDY, 256, 3, 2>(p, 3, st); break;
+    case 4: e = launch_top_tile<RC, PAW / 2, NDY, 256, 3, 2>(p, 3, st); break;
+    default: e = launch_top_tile<RC, PAW, NDY, 256, 3, 1>(p, 4, st); break;
   }
   if (e != cudaSuccess) return e;
+  if (L >= 5) {
+    e = launch_refine<RC, NB_REF, NDY, THR_REF, 4, 2>(p, 3, st);
+    if (e != cudaSuccess) return e;
+  }
   if (L >= 4) {
     e = launch_refine<RC, NB_REF, NDY, THR_REF, 4, 4>(p, 2, st);
     if (e != cudaSuccess) return e;
@@ -1065,10 +1071,12 @@ static cudaError_t launch_pool(const HbmaParams& p, cudaStream_t st) {
 bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int* extra_launches) {
   static const bool off = getenv("SVC_HBMA_NO_POOL") != nullptr;  // experiment hook
   const uint32_t L = p.lay.levels, r = p.r;
+  // r <= 4: hbma_tile_kernel, or (5 levels, r = 3, 4: the reach does not fit a tile) the warp-per-block
+  // window kernel of k_hbma.cu, which measures faster than per-level launches on such small windows
   if (off || p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > (L == 1 ? 112u : 64u)) return false;
   if ((uint64_t)p.mvw * p.mvh * p.n_frames > 0x7fffffffull) return false;
   static const bool no_levels = getenv("SVC_HBMA_NO_LEVELS") != nullptr;  // experiment hook
-  if (L >= 2 && L <= 4 && r <= 32 && p.mv && p.mad && !no_levels && getenv("SVC_HBMA_FORCE_POOL") == nullptr) {
+  if (L >= 2 && r <= 32 && p.mv && p.mad && !no_levels && getenv("SVC_HBMA_FORCE_POOL") == nullptr) {
     // one launch per level; <range class, candidate rows per item, blocks per CTA and CTAs per SM of
     // the 16x16 refinement level>
     static const char* env_lv = getenv("SVC_HBMA_POOL_VARIANT");  // tuning hook

@@ -158,10 +158,11 @@ def test_hbma_pooled_window_path_vs_oracle(gpu, oracle, L, R, w, h, monkeypatch)
 
 
 @pytest.mark.parametrize("L,R", [(2, 10), (2, 16), (2, 27), (2, 32), (2, 50), (2, 64), (3, 20), (3, 32), (3, 45),
-                                 (3, 64), (3, 100), (3, 128), (4, 40), (4, 64), (4, 100), (4, 128), (4, 200), (4, 256)])
+                                 (3, 64), (3, 100), (3, 128), (4, 40), (4, 64), (4, 100), (4, 128), (4, 200), (4, 256),
+                                 (5, 48), (5, 64), (5, 80), (5, 128), (5, 300), (5, 512)])
 @pytest.mark.parametrize("w,h", [(416, 240), (48, 176)])
 def test_hbma_level_synchronous_path_vs_oracle(gpu, oracle, L, R, w, h):
-    """2..4 levels, top-level range 5..32: one launch per level (shared-window tile kernel at the top
+    """2..5 levels, top-level range 5..32 (3..32 for 5 levels): one launch per level (shared-window tile kernel at the top
     level, single-level refinement kernels below), the coarser level's vector and MAD carried through
     the output arrays -- partial tiles, frames narrower than a window, flat-patch ties, the
     zero-vector rule of the top level and the strict '<' of the refinement levels."""
