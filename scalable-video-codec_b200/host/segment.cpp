@@ -442,6 +442,10 @@ const char* ValidateSegmentConfig(const SegmentConfig& c) {
 
 MotionSegmenter::MotionSegmenter(const SegmentConfig& cfg, uint w, uint h) : cfg_(cfg), w_(w), h_(h) {
   const size_t n = (size_t)w * h;
+  // the reference asserts motion_field_sz >= subset_sz (libs/motion.cpp:196); with fewer vectors its
+  // distinct-subset draw never terminates
+  if (n < cfg.ransac.subset_sz || cfg.ransac.subset_sz == 0)
+    throw Error(1, "motion field smaller than the RANSAC subset size");
   mask_.resize(n);
   cluster_mask_.resize(n);
   comp_ids_.resize(n);
