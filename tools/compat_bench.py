@@ -40,6 +40,38 @@ def main():
     res["svc_dct_planar ms"] = t_of(lambda: svc.dct_planar(fr[1], pw, ph), 10)
     res["oracle dct_planar (C port) ms"] = t_of(lambda: O.dct_planar(fr[1], pw, ph), 2)
     res["svc_encode_frame_stream ms"] = t_of(lambda: svc.encode_frame_stream(fr[1], pw, ph), 10)
+    # "as shipped" comparators: the OpenCV calls the reference makes, one thread
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        bgr = fr[1]
+
+        def cv_k1():
+            padded = cv2.copyMakeBorder(bgr, 0, ph - h, 0, pw - w, cv2.BORDER_CONSTANT, value=0)  # libs/encoder.cpp:459-461
+            y = cv2.extractChannel(cv2.cvtColor(padded, cv2.COLOR_BGR2YUV), 0)                     # :468-469
+            pyr = [y]
+            for _ in range(3):                                                                     # :470 (buildPyramid)
+                pyr.append(cv2.pyrDown(pyr[-1]))
+            return pyr
+
+        def cv_dct():
+            planes = cv2.split(cv2.copyMakeBorder(bgr, 0, ph - h, 0, pw - w, cv2.BORDER_CONSTANT, value=0)
+                               .astype(np.float32))                                                # :638, :328
+            for pl in planes:                                                                      # :329-337
+                for by in range(0, ph, 8):
+                    for bx in range(0, pw, 8):
+                        pl[by:by + 8, bx:bx + 8] = cv2.dct(pl[by:by + 8, bx:bx + 8])
+            return planes
+
+        res["cv2 copyMakeBorder+cvtColor+extractChannel+3x pyrDown ms (1 thread)"] = t_of(cv_k1, 5)
+        t0 = time.perf_counter()
+        cv_dct()
+        res["cv2.dct per 8x8 block, 97 920 calls ms (1 thread, python call overhead included)"] = \
+            (time.perf_counter() - t0) * 1e3
+        res["opencv"] = cv2.__version__
+    except ImportError:
+        pass
+    res["host_cpus"] = os.cpu_count()
     print(json.dumps(res, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "compat_bench.json"), "w"), indent=1)
