@@ -141,3 +141,80 @@ def test_encoder_app_block_types_follow_the_reference_chain(gpu, oracle, tmp_pat
         assert np.array_equal(got, exp[(by * 8 // 16) * mw + bx * 8 // 16])
         any_fg |= bool(got.any())
     assert any_fg
+
+
+DEC = os.path.join(PKG, "bin", "svc_decoder")
+
+
+def _build_decoder():
+    subprocess.run(["make", "-C", PKG, "bin/svc_decoder"], check=True, stdout=subprocess.DEVNULL)
+
+
+def test_decoder_app_validates_like_the_reference(oracle):
+    """Validate(DecoderConfig) messages (libs/decoder.cpp:35-47), short header, and the streams this
+    decoder refuses: other transform blocks, horizontally padded frames."""
+    _build_decoder()
+    run = lambda args, data=b"": subprocess.run([DEC] + args, input=data, capture_output=True, timeout=60)
+    assert run([]).returncode != 0
+    r = run(["--foreground-quant-step", "0", "-"])
+    assert r.returncode != 0 and b"invalid foreground quantization step" in r.stderr
+    r = run(["--background-quant-step", "0", "-"])
+    assert r.returncode != 0 and b"invalid background quantization step" in r.stderr
+    r = run(["-"], b"short")
+    assert r.returncode != 0 and b"header" in r.stderr
+    hdr = oracle.header(3, 1000, 600, 1008, 608).tobytes()  # 1000 -> 1008: horizontal padding
+    r = run(["-"], hdr)
+    assert r.returncode != 0 and b"not decodable" in r.stderr
+    hdr = oracle.header(3, 64, 64, 64, 64, tbw=4, tbh=4).tobytes()
+    r = run(["-"], hdr)
+    assert r.returncode != 0 and b"8x8" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,gaze", [(320, 176, None), (320, 180, (100, 60)), (1920, 1080, (960, 1070))])
+def test_encoder_app_piped_into_decoder_app(gpu, oracle, tmp_path, w, h, gaze):
+    """svc_encoder | svc_decoder: every decoded frame equals the oracle's ParseBlock + DecodeBlock
+    (libs/decoder.cpp:102-149) of the same records, rounded to 8 bits; at 1080p / 180 rows the encoder
+    writes fewer block rows than the padded frame holds and the rest stays black."""
+    import numpy as np
+    from svc_b200.synth import SyntheticSequence
+    _build_app()
+    _build_decoder()
+    n = 4
+    frames = SyntheticSequence(w, h, n, seed=w + h).frames()
+    raw = tmp_path / "in.bgr"
+    raw.write_bytes(frames.tobytes())
+    r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "3", "--verbose", "0",
+                        "--seed", "3", str(raw)], capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    stream = r.stdout
+    fg, bg = 2, 24
+    base = ["--foreground-quant-step", str(fg), "--background-quant-step", str(bg), "--batch", "3",
+            "--verbose", "0"]
+    if gaze:
+        base += ["--gaze-x", str(gaze[0]), "--gaze-y", str(gaze[1])]
+    d = subprocess.run([DEC] + base + ["--padded", "1", "-"], input=stream, capture_output=True, timeout=300)
+    assert d.returncode == 0, d.stderr
+    pw, ph = oracle.padded_dim(w, 16, 4), oracle.padded_dim(h, 16, 4)
+    out = np.frombuffer(d.stdout, np.uint8).reshape(n - 1, ph, pw, 3)
+    fb = oracle.serialized_frame_bytes(w, h)
+    rows = (h + 7) // 8 * 8  # block rows the encoder wrote
+    gz = oracle.gaze_rect(gaze[0], gaze[1], 64, 64, w, h, pw, ph) if gaze else None
+    if gz is not None and gz[1] + gz[3] > rows:  # the oracle decodes the written rows only
+        gz = (gz[0], gz[1], gz[2], max(0, rows - gz[1]))
+    step = 1 if w * h < 500 * 500 else n - 2   # the oracle's per-block loop is slow at 1080p
+    for t in range(0, n - 1, step):
+        rec = np.frombuffer(stream, np.uint8, fb, 32 + t * fb)
+        exp = oracle.decode_frame_blocks(rec, pw, rows, fg_q=fg, bg_q=bg, gaze=gz)
+        exp8 = np.clip(np.rint(exp), 0, 255)
+        got = out[t, :rows].astype(np.float32)
+        # a float error <= 1e-3 can flip the 8-bit rounding only next to .5: allow those, nothing else
+        diff = np.abs(got - exp8)
+        near_half = np.abs(np.abs(exp - np.floor(exp)) - 0.5) < 2e-3
+        assert diff.max() <= 1 and not (diff > 0)[~near_half].any()
+        assert not out[t, rows:].any()
+    # cropped output (the default): the same pixels without the padding
+    d2 = subprocess.run([DEC] + base + ["-"], input=stream, capture_output=True, timeout=300)
+    assert d2.returncode == 0, d2.stderr
+    crop = np.frombuffer(d2.stdout, np.uint8).reshape(n - 1, h, w, 3)
+    assert np.array_equal(crop, out[:, :h, :w])
