@@ -284,6 +284,254 @@ dct8x8_stream_kernel(const DctParams p, const uint32_t nbx, const uint32_t nby_s
   }
 }
 
+// ---- fused stream kernels for 16x16 and 4x4 transform blocks -------------------------
+// Same contract as dct8x8_stream_kernel (Dct + SerializeEncodedFrame, optional level-0 luma, one
+// contiguous TMA bulk store per unit of consecutive records) for the other square transform
+// blocks the encoder accepts by default geometry (libs/encoder.cpp:119-139: any block that
+// divides the 16x16 motion block).  Needs w == pw like the 8x8 kernel, so that the serializer's
+// unpadded row stride and swapped loop bounds (libs/encoder.cpp:257-262) coincide with the plane.
+
+// 8-point transform of the even half of a 16-point one: every factor times 1/sqrt(2); `dc_off`
+// is what the DC sum carries when the inputs are magic floats (0 otherwise).
+__device__ __forceinline__ void dct8_half(const float (&s)[8], float (&o)[8], const float dc_off) {
+  constexpr float k = 0.70710678118654752440f;
+  const float s0 = s[0] + s[7], s1 = s[1] + s[6], s2 = s[2] + s[5], s3 = s[3] + s[4];
+  const float d0 = s[0] - s[7], d1 = s[1] - s[6], d2 = s[2] - s[5], d3 = s[3] - s[4];
+  const float e0 = s0 + s3, e1 = s1 + s2, e2 = s0 - s3, e3 = s1 - s2;
+  o[0] = (SVC_C4 * k) * ((e0 + e1) - dc_off);
+  o[4] = (SVC_C4 * k) * (e0 - e1);
+  o[2] = fmaf(SVC_B2 * k, e2, (SVC_B6 * k) * e3);
+  o[6] = fmaf(SVC_B6 * k, e2, -(SVC_B2 * k) * e3);
+  o[1] = fmaf(SVC_A * k, d0, fmaf(SVC_B * k, d1, fmaf(SVC_C * k, d2, (SVC_D * k) * d3)));
+  o[3] = fmaf(SVC_B * k, d0, fmaf(-SVC_D * k, d1, fmaf(-SVC_A * k, d2, -(SVC_C * k) * d3)));
+  o[5] = fmaf(SVC_C * k, d0, fmaf(-SVC_A * k, d1, fmaf(SVC_D * k, d2, (SVC_B * k) * d3)));
+  o[7] = fmaf(SVC_D * k, d0, fmaf(-SVC_C * k, d1, fmaf(SVC_B * k, d2, -(SVC_A * k) * d3)));
+}
+
+// sqrt(2/16) cos(pi q / 32), q = 1, 3, .., 15
+__device__ __forceinline__ constexpr float dct16_odd_factor(int i, int m) {
+  constexpr float K[8] = {0.35185093438159565f, 0.33832950029358816f, 0.31180625324666783f,
+                          0.2733004667504394f,  0.2242918965856591f,  0.1666639146194367f,
+                          0.10263113188058934f, 0.034654292299772925f};
+  int q = ((2 * i + 1) * (2 * m + 1)) % 64;  // cos(pi q / 32), q odd
+  if (q > 32) q = 64 - q;
+  const bool neg = q > 16;
+  if (neg) q = 32 - q;
+  return neg ? -K[(q - 1) / 2] : K[(q - 1) / 2];
+}
+
+// 16-point orthonormal DCT-II: X[2m] = DCT8(x_i + x_{15-i})[m] / sqrt 2, X[2m+1] = 8x8 odd matrix
+// on x_i - x_{15-i} (exact differences, so magic-float inputs need no correction there).
+__device__ __forceinline__ void dct16(const float (&x)[16], float (&X)[16], const float dc_off) {
+  float s[8], d[8], e[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = x[i] + x[15 - i]; d[i] = x[i] - x[15 - i]; }
+  dct8_half(s, e, dc_off);
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    X[2 * m] = e[m];
+    float acc = dct16_odd_factor(0, m) * d[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) acc = fmaf(dct16_odd_factor(i, m), d[i], acc);
+    X[2 * m + 1] = acc;
+  }
+}
+
+constexpr int kRecWords16 = 1 + 3 * 256;  // 3076-byte record
+constexpr int kUnit16 = 8;                // records per CTA (24.6 KB of staging)
+constexpr int kTmp16Blk = 16 * 17;        // one channel of one block, row pitch 17; 272 = 16 (mod 32):
+                                          // the two blocks of a warp use disjoint banks
+constexpr int kTmp16Buf = kUnit16 * kTmp16Blk;
+
+// shared -> global hand-over of a unit's contiguous record span (TMA bulk store when 16-byte
+// aligned, cooperative word copy otherwise); all threads of the CTA call it
+__device__ __forceinline__ void store_span(const uint32_t* stage, uint8_t* dst, const uint32_t bytes) {
+  const bool bulk_ok = ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) && ((bytes & 15u) == 0);
+  if (bulk_ok) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(stage);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(dst), "r"(s_addr), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    __syncthreads();
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+    for (uint32_t k = threadIdx.x; k < bytes / 4u; k += blockDim.x) d32[k] = stage[k];
+  }
+}
+
+// CTA = 128 threads = one unit of 8 consecutive 16x16 blocks in serializer order.  Row pass:
+// thread (block, row) loads the row's 48 interleaved bytes once (3 x 128 bit), emits its 16 luma
+// bytes (kWithY) and the 16-point transform of each channel into a padded scratch tile; column
+// pass: thread (block, column) transforms the three channels' columns and writes the coefficients
+// at their place in the record.  Then one bulk store of the 8-record span.
+template <bool kWithY>
+__global__ void __launch_bounds__(128)
+dct16x16_stream_kernel(const DctParams p, const uint32_t nbx, const uint32_t nby_stream,
+                       const uint32_t nby_total, const YOut yo) {
+  __shared__ __align__(128) uint32_t stage[kUnit16 * kRecWords16];
+  __shared__ float tmp[2 * kTmp16Buf];
+  const uint32_t t = threadIdx.x, b = t >> 4, r = t & 15u;
+  const uint32_t per_frame = nbx * nby_total, per_stream = nbx * nby_stream;
+  const uint32_t chunks_per_frame = (per_frame + kUnit16 - 1u) / kUnit16;
+  const uint32_t f = blockIdx.x / chunks_per_frame;
+  const uint32_t n0 = (blockIdx.x % chunks_per_frame) * kUnit16;
+  const uint32_t n = n0 + b;
+  const bool active = n < per_frame;
+  const uint32_t tbx = active ? n % nbx : 0u, tby = active ? n / nbx : 0u;
+  const uint32_t px = tbx * 16u, py = tby * 16u;
+
+  uint32_t raw[12];
+  {
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
+    if (active && py + r < p.h) {  // whole rows below the frame are the zero padding
+      const uint4* q = reinterpret_cast<const uint4*>(p.bgr + (((uint64_t)f * p.h + py + r) * p.w + px) * 3u);
+      v0 = __ldg(q); v1 = __ldg(q + 1); v2 = __ldg(q + 2);
+    }
+    raw[0] = v0.x; raw[1] = v0.y; raw[2] = v0.z; raw[3] = v0.w;
+    raw[4] = v1.x; raw[5] = v1.y; raw[6] = v1.z; raw[7] = v1.w;
+    raw[8] = v2.x; raw[9] = v2.y; raw[10] = v2.z; raw[11] = v2.w;
+  }
+  if (kWithY && active) {
+    const uint32_t lo[6] = {raw[0], raw[1], raw[2], raw[3], raw[4], raw[5]};
+    const uint32_t hi[6] = {raw[6], raw[7], raw[8], raw[9], raw[10], raw[11]};
+    const uint2 y0 = luma_row8(lo), y1 = luma_row8(hi);
+    uint8_t* yrow = yo.l0 + (uint64_t)(yo.first_slot + f) * yo.slot_bytes + (uint64_t)(py + r) * yo.pitch + px;
+    *reinterpret_cast<uint4*>(yrow) = make_uint4(y0.x, y0.y, y1.x, y1.y);
+  }
+  if (n0 >= per_stream) return;  // CTA-uniform: padded block rows carry no record
+
+  uint32_t* rec = stage + b * kRecWords16;
+  if (r == 0) {
+    uint32_t bt = 0;
+    if (p.block_types && n < per_stream)
+      bt = __ldg(p.block_types + (uint64_t)f * p.mv_field_w * p.mv_field_h +
+                 (py / p.mv_block_h) * p.mv_field_w + px / p.mv_block_w);
+    rec[0] = bt;
+  }
+  // channel c: row pass (thread = row r of block b) into scratch buffer c & 1, barrier, column pass
+  // (thread = column r of block b) into the record.  One barrier per channel is enough: whoever
+  // writes buffer c & 1 again (channel c + 2) has passed the barrier of channel c + 1, which every
+  // thread reaches only after its column pass of channel c.  The row is shifted down one byte per
+  // channel so that one code path (channel at byte 3j) serves B, G and R.
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    float* buf = tmp + (c & 1) * kTmp16Buf + b * kTmp16Blk;
+    {
+      float x[16], X[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = byte_to_magic(raw[(3 * j) >> 2], (3 * j) & 3);
+      dct16(x, X, 524288.0f);  // 8 sums of two magic floats: 8 * 2^16
+      float* trow = buf + r * 17u;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) trow[k] = X[k];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) raw[k] = __funnelshift_r(raw[k], raw[k + 1], 8);
+      raw[11] >>= 8;
+    }
+    __syncthreads();
+    {
+      const float* tcol = buf + r;
+      float x[16], X[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = tcol[j * 17];
+      dct16(x, X, 0.f);
+      uint32_t* o = rec + 1 + c * 256 + r;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) o[k * 16] = __float_as_uint(X[k]);
+    }
+  }
+  const uint32_t n_act = min((uint32_t)kUnit16, per_stream - n0);
+  store_span(stage, p.stream + (uint64_t)f * p.frame_stream_bytes + (uint64_t)n0 * (kRecWords16 * 4u),
+             n_act * kRecWords16 * 4u);
+}
+
+// 4-point orthonormal DCT-II
+__device__ __forceinline__ void dct4(float& x0, float& x1, float& x2, float& x3, const float dc_off) {
+  constexpr float a = 0.6532814824381883f, bq = 0.27059805007309856f;  // sqrt(1/2) cos(pi/8), cos(3 pi/8)
+  const float s0 = x0 + x3, s1 = x1 + x2, d0 = x0 - x3, d1 = x1 - x2;
+  x0 = 0.5f * ((s0 + s1) - dc_off);
+  x2 = 0.5f * (s0 - s1);
+  x1 = fmaf(a, d0, bq * d1);
+  x3 = fmaf(bq, d0, -a * d1);
+}
+
+constexpr int kRecWords4 = 1 + 3 * 16;  // 196-byte record
+constexpr int kUnit4 = 128;             // records per CTA (24.5 KB of staging)
+
+// One lane = one 4x4 block (4 rows x 12 interleaved bytes, three channels in registers); a CTA of
+// 128 lanes assembles 128 consecutive records (lane * 49 + const: conflict free) and hands the span
+// to the TMA engine.
+template <bool kWithY>
+__global__ void __launch_bounds__(kUnit4)
+dct4x4_stream_kernel(const DctParams p, const uint32_t nbx, const uint32_t nby_stream,
+                     const uint32_t nby_total, const YOut yo) {
+  __shared__ __align__(128) uint32_t stage[kUnit4 * kRecWords4];
+  const uint32_t per_frame = nbx * nby_total, per_stream = nbx * nby_stream;
+  const uint32_t chunks_per_frame = (per_frame + kUnit4 - 1u) / kUnit4;
+  const uint32_t f = blockIdx.x / chunks_per_frame;
+  const uint32_t n0 = (blockIdx.x % chunks_per_frame) * kUnit4;
+  const uint32_t n = n0 + threadIdx.x;
+  const bool active = n < per_frame;
+  const uint32_t tbx = active ? n % nbx : 0u, tby = active ? n / nbx : 0u;
+  const uint32_t px = tbx * 4u, py = tby * 4u;
+  uint32_t raw[4][3];
+  {
+    const uint8_t* q0 = p.bgr + (((uint64_t)f * p.h + py) * p.w + px) * 3u;
+    const uint64_t row_bytes = (uint64_t)p.w * 3u;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      raw[r][0] = raw[r][1] = raw[r][2] = 0u;
+      if (active && py + r < p.h) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(q0 + r * row_bytes);
+        raw[r][0] = __ldg(q); raw[r][1] = __ldg(q + 1); raw[r][2] = __ldg(q + 2);
+      }
+    }
+  }
+  if (kWithY && active) {
+    uint8_t* yrow = yo.l0 + (uint64_t)(yo.first_slot + f) * yo.slot_bytes + (uint64_t)py * yo.pitch + px;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t (&w)[3] = raw[r];
+      const uint32_t y0 = luma_q14(w[0]), y1 = luma_q14(__funnelshift_r(w[0], w[1], 24));
+      const uint32_t y2 = luma_q14(__funnelshift_r(w[1], w[2], 16)), y3 = luma_q14(w[2] >> 8);
+      *reinterpret_cast<uint32_t*>(yrow + (uint64_t)r * yo.pitch) = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+    }
+  }
+  if (n0 >= per_stream) return;
+  uint32_t* rec = stage + threadIdx.x * kRecWords4;
+  {
+    uint32_t bt = 0;
+    if (p.block_types && n < per_stream)
+      bt = __ldg(p.block_types + (uint64_t)f * p.mv_field_w * p.mv_field_h +
+                 (py / p.mv_block_h) * p.mv_field_w + px / p.mv_block_w);
+    rec[0] = bt;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[r][j] = byte_to_magic(raw[r][(3 * j + c) >> 2], (3 * j + c) & 3);
+      dct4(v[r][0], v[r][1], v[r][2], v[r][3], 131072.0f);  // 4 * 2^15
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dct4(v[0][j], v[1][j], v[2][j], v[3][j], 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rec[1 + c * 16 + u * 4 + j] = __float_as_uint(v[u][j]);
+  }
+  const uint32_t n_act = min((uint32_t)kUnit4, per_stream - n0);
+  store_span(stage, p.stream + (uint64_t)f * p.frame_stream_bytes + (uint64_t)n0 * (kRecWords4 * 4u),
+             n_act * kRecWords4 * 4u);
+}
+
 // ---- generic separable path (any transform block up to 32 x 32) ---------------
 // out = Ch . X . Cw^T per block, C[k][n] = s_k cos(pi (2n+1) k / (2N)) (cv::dct, libs/encoder.cpp:335).
 // One CTA transforms a tile of whole blocks of one channel in shared memory: the tile's pixels are
@@ -491,18 +739,27 @@ static cudaError_t planar_into(const DctParams& p, const uint8_t* bgr, uint32_t 
 
 cudaError_t prepare_dct_kernels() {
   // the staging buffers want the large shared-memory carve-out (9 CTAs x 24.7 KB)
-  cudaError_t e = cudaFuncSetAttribute(dct8x8_stream_kernel<true>,
-                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dct8x8_stream_kernel<false>,
-                              cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  const void* fns[] = {(const void*)dct8x8_stream_kernel<true>,   (const void*)dct8x8_stream_kernel<false>,
+                       (const void*)dct16x16_stream_kernel<true>, (const void*)dct16x16_stream_kernel<false>,
+                       (const void*)dct4x4_stream_kernel<true>,   (const void*)dct4x4_stream_kernel<false>};
+  for (const void* fn : fns) {
+    const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
-// the fused stream kernel: 8x8 blocks, no horizontal padding (so the serializer's
-// unpadded row stride equals the plane stride), 8-byte aligned 24-byte block rows
+// the fused stream kernels: square 8x8 / 16x16 / 4x4 blocks, no horizontal padding (so the
+// serializer's unpadded row stride equals the plane stride), block rows aligned for vector loads
 static bool dct_fast_stream_ok(const DctParams& p) {
-  return p.tbw == 8 && p.tbh == 8 && p.w == p.pw && (p.w % 8u) == 0 &&
-         (reinterpret_cast<uintptr_t>(p.bgr) & 7u) == 0;
+  if (p.tbw != p.tbh || p.w != p.pw) return false;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p.bgr);
+  switch (p.tbw) {
+    case 8: return (p.w % 8u) == 0 && (a & 7u) == 0;
+    case 16: return (p.w % 16u) == 0 && (a & 15u) == 0;
+    case 4: return (p.w % 4u) == 0 && (a & 3u) == 0;
+    default: return false;
+  }
 }
 
 bool dct_needs_scratch(const DctParams& p) {
@@ -511,7 +768,7 @@ bool dct_needs_scratch(const DctParams& p) {
 }
 
 bool dct_can_fuse_y(const DctParams& p) {
-  return p.stream && dct_fast_stream_ok(p) && (p.ph % 8u) == 0;
+  return p.stream && dct_fast_stream_ok(p) && (p.ph % p.tbh) == 0;
 }
 
 cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* nl) {
@@ -536,17 +793,24 @@ cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* nl) {
   }
   if (p.stream) {
     if (dct_fast_stream_ok(p)) {
-      const uint32_t nbx = p.w / 8, nby = (p.h + 7) / 8;
+      const uint32_t tb = p.tbw, unit = tb == 8 ? 32u : (tb == 16 ? (uint32_t)kUnit16 : (uint32_t)kUnit4);
+      const uint32_t nbx = p.w / tb, nby = (p.h + tb - 1) / tb;
       const bool with_y = p.y_l0 != nullptr;
-      const uint32_t nby_total = with_y ? p.ph / 8 : nby;
-      const uint64_t units = (uint64_t)((nbx * nby_total + 31) / 32) * p.n_frames;
+      const uint32_t nby_total = with_y ? p.ph / tb : nby;
+      const uint64_t units = (uint64_t)((nbx * nby_total + unit - 1) / unit) * p.n_frames;
       if (units > 0x7fffffffull) return cudaErrorInvalidValue;
       YOut yo{p.y_l0, p.y_slot_bytes, p.y_first_slot, p.y_pitch};
       // occupancy knob (experiment hook): extra dynamic shared memory per CTA leaves room on the
       // SM for the motion-stream kernels that run concurrently
       static const char* env_pad = getenv("SVC_DCT_SMEM_PAD");
       const size_t pad = env_pad ? (size_t)atoi(env_pad) : 0;
-      if (with_y) dct8x8_stream_kernel<true><<<(uint32_t)units, 96, pad, st>>>(p, nbx, nby, nby_total, yo);
+      if (tb == 16) {
+        if (with_y) dct16x16_stream_kernel<true><<<(uint32_t)units, 128, 0, st>>>(p, nbx, nby, nby_total, yo);
+        else dct16x16_stream_kernel<false><<<(uint32_t)units, 128, 0, st>>>(p, nbx, nby, nby_total, yo);
+      } else if (tb == 4) {
+        if (with_y) dct4x4_stream_kernel<true><<<(uint32_t)units, kUnit4, 0, st>>>(p, nbx, nby, nby_total, yo);
+        else dct4x4_stream_kernel<false><<<(uint32_t)units, kUnit4, 0, st>>>(p, nbx, nby, nby_total, yo);
+      } else if (with_y) dct8x8_stream_kernel<true><<<(uint32_t)units, 96, pad, st>>>(p, nbx, nby, nby_total, yo);
       else dct8x8_stream_kernel<false><<<(uint32_t)units, 96, pad, st>>>(p, nbx, nby, nby_total, yo);
       if (nl) *nl += 1;
       e = cudaGetLastError();

@@ -87,3 +87,32 @@ def test_random_wide_range_session(gpu, oracle, cfg):
             emv, emad = oracle.hbma(pyr[i - 1], pyr[i], R)
             assert np.array_equal(mv[i - 1], emv), (cfg, i)
             assert np.array_equal(mad[i - 1], emad), (cfg, i)
+
+
+@pytest.mark.parametrize("w,h,mb,L,tb,n,batch", [(320, 180, 16, 4, 16, 5, 3), (320, 176, 16, 4, 4, 4, 2),
+                                                  (64, 40, 16, 3, 16, 3, 1), (200, 90, 8, 3, 4, 4, 3),
+                                                  (1920, 1080, 16, 4, 16, 3, 2), (960, 540, 16, 4, 4, 3, 2)])
+def test_session_fused_square_transform_blocks(gpu, oracle, w, h, mb, L, tb, n, batch):
+    """Frames without horizontal padding and 16x16 / 4x4 transform blocks: the fused stream kernels
+    (records + level-0 luma in one pass) inside a session -- the motion field checks their luma."""
+    frames = SyntheticSequence(w, h, n, seed=w + 3 * h + tb, n_rects=3).frames()
+    sc = gpu.SessionConfig(frame_w=w, frame_h=h, mv_block_w=mb, mv_block_h=mb, pyr_lvl_count=L,
+                           mv_search_range=1 << (L - 1), transform_block_w=tb, transform_block_h=tb,
+                           max_batch=batch)
+    with gpu.Session(sc) as s:
+        pw, ph = s.padded_w, s.padded_h
+        assert pw == w
+        rng = np.random.default_rng(11)
+        bt = rng.integers(0, 5, size=(n - 1, s.mv_field_h * s.mv_field_w)).astype(np.uint32)
+        mv, mad, st = s.encode(frames, block_types=bt)
+        rec = 1 + 3 * tb * tb
+        pyr = [oracle.y_pyramid(f, pw, ph, L) for f in frames]
+        for i in range(1, n):
+            emv, emad = oracle.hbma(pyr[i - 1], pyr[i], 1 << (L - 1), mb, mb)
+            assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad), i
+            planes = oracle.dct_planar(frames[i], pw, ph, tb, tb)
+            exp = oracle.serialize_frame(planes, bt[i - 1], w, h, tb, tb, pw // mb, mb, mb)
+            g = st[i - 1].view(np.uint32).reshape(-1, rec)
+            e = exp.view(np.uint32).reshape(-1, rec)
+            assert np.array_equal(g[:, 0], e[:, 0]), i
+            assert np.abs(g[:, 1:].view(np.float32) - e[:, 1:].view(np.float32)).max() <= DCT_TOL, i

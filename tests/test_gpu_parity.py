@@ -294,7 +294,11 @@ def _stream_check(gpu, oracle, f, pw, ph, tbw, tbh, bt):
 
 @pytest.mark.parametrize("w,h,tbw,tbh", [(160, 92, 8, 8), (104, 56, 8, 8), (1920, 1080, 8, 8),
                                          (960, 540, 8, 8), (48, 40, 8, 8), (96, 48, 4, 4),
-                                         (80, 48, 8, 4), (100, 36, 16, 16)])
+                                         (80, 48, 8, 4), (100, 36, 16, 16),
+                                         # fused 16x16 / 4x4 stream kernels (w == padded w)
+                                         (160, 92, 16, 16), (64, 64, 16, 16), (1920, 1080, 16, 16),
+                                         (16, 16, 16, 16), (48, 40, 4, 4), (176, 130, 4, 4), (1920, 1080, 4, 4),
+                                         (2000, 48, 4, 4)])
 def test_stream_layout_vs_oracle(gpu, oracle, w, h, tbw, tbh):
     rng = np.random.default_rng(w * 3 + h + tbw)
     f = rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8)

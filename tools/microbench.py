@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16, help="frames per launch")
     ap.add_argument("--sets", type=int, default=8, help="distinct input sets cycled through (>> L2)")
     ap.add_argument("--iters", type=int, default=104)
+    ap.add_argument("--tb", type=int, default=8, help="square transform block (8: default; 16 / 4: fused variants)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "microbench_4k.json"))
     a = ap.parse_args()
     import torch
@@ -36,7 +37,9 @@ def main():
     W, H, F, S = a.width, a.height, a.frames, a.sets
     torch.cuda.set_device(0)
     ts = torch.cuda.Stream()
-    sess = svc.Session(svc.SessionConfig(frame_w=W, frame_h=H, max_batch=F, cuda_stream=ts.cuda_stream))
+    TB = a.tb
+    sess = svc.Session(svc.SessionConfig(frame_w=W, frame_h=H, max_batch=F, cuda_stream=ts.cuda_stream,
+                                         transform_block_w=TB, transform_block_h=TB))
     fin, fst = sess.frame_in_bytes, sess.frame_stream_bytes
     P = sess.padded_w * sess.padded_h
     seq = svc.SyntheticSequence(W, H, F, seed=99)
@@ -71,7 +74,7 @@ def main():
     b = F * (sum(P >> (2 * l) for l in range(3)) + sum(P >> (2 * l) for l in range(1, 4)))
     res["K1b_pyr_down_only"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
                                 "note": "F frames = %.0f MB of pyramids: L2 resident between launches" % (b / 1e6)}
-    if (W, H) == (sess.padded_w, sess.padded_h):
+    if (W, H) == (sess.padded_w, sess.padded_h) and TB == 8:
         ms = timed(lambda i: svc.decode_frames_device(0, ts.cuda_stream, d_st.data_ptr() + (i % S) * F * fst, F,
                                                       W, H, d_px.data_ptr() + (i % 2) * F * P * 3 * 4,
                                                       fg_quant_step=1, bg_quant_step=640))
@@ -81,15 +84,16 @@ def main():
     torch.cuda.synchronize()
     fr = seq.frame(0)
     st = d_st[:fst].cpu().numpy()
-    nbx = W // 8
-    rec = st.view(np.uint32).reshape(-1, nbx, 193)
+    nbx = W // TB
+    rec = st.view(np.uint32).reshape(-1, nbx, 1 + 3 * TB * TB)
     crop = np.ascontiguousarray(fr[512:576, 1024:1152])
-    planes = O.dct_planar(crop, 128, 64)
-    got = rec[64:72, 128:144, 1:].view(np.float32).reshape(8, 16, 3, 8, 8)
-    exp = planes.reshape(3, 8, 8, 16, 8).transpose(1, 3, 0, 2, 4)
+    planes = O.dct_planar(crop, 128, 64, TB, TB)
+    by, bx = 64 // TB, 128 // TB
+    got = rec[512 // TB:512 // TB + by, 1024 // TB:1024 // TB + bx, 1:].view(np.float32).reshape(by, bx, 3, TB, TB)
+    exp = planes.reshape(3, by, TB, bx, TB).transpose(1, 3, 0, 2, 4)
     res["dct_max_abs_err_vs_oracle"] = float(np.abs(got - exp).max())
     out = {"gpu": torch.cuda.get_device_name(0), "width": W, "height": H, "frames_per_launch": F,
-           "iters": a.iters, "hbm_peak_gbs": peak, "results": res}
+           "iters": a.iters, "transform_block": TB, "hbm_peak_gbs": peak, "results": res}
     print(json.dumps(out, indent=1))
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(out, open(a.out, "w"), indent=1)
