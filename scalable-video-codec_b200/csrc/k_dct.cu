@@ -339,9 +339,17 @@ __device__ __forceinline__ void dct16(const float (&x)[16], float (&X)[16], cons
 
 constexpr int kRecWords16 = 1 + 3 * 256;  // 3076-byte record
 constexpr int kUnit16 = 8;                // records per CTA (24.6 KB of staging)
-constexpr int kTmp16Blk = 16 * 17;        // one channel of one block, row pitch 17; 272 = 16 (mod 32):
-                                          // the two blocks of a warp use disjoint banks
+constexpr int kTmp16Pitch = 20;           // scratch tile [frequency k][row r]: 16 floats + 4 of padding, so the
+                                          // column pass reads its 16 values as 4 conflict-free 128-bit loads
+// A warp serves blocks w and w + 4 of the unit (16 lanes each).  Their scratch tiles and their records
+// sit 16 banks apart, so that every shared-memory access of the two passes is conflict free:
+// 4 * 324 = 16 (mod 32) for the tiles; the records of blocks 4..7 start 12 words after those of
+// blocks 0..3 end (4 * 769 + 12 = 16 (mod 32)), and each half leaves as its own bulk store.
+constexpr int kTmp16Blk = 16 * kTmp16Pitch + 4;
 constexpr int kTmp16Buf = kUnit16 * kTmp16Blk;
+constexpr int kStageHalf16 = 4 * kRecWords16 + 12;
+constexpr int kIter16 = 2;                // consecutive units per CTA: the next unit's pixels are in flight during
+                                          // the transforms (6 CTAs per SM: 35.4 KB of shared memory, 80 registers)
 
 // shared -> global hand-over of a unit's contiguous record span (TMA bulk store when 16-byte
 // aligned, cooperative word copy otherwise); all threads of the CTA call it
@@ -364,90 +372,136 @@ __device__ __forceinline__ void store_span(const uint32_t* stage, uint8_t* dst, 
   }
 }
 
-// CTA = 128 threads = one unit of 8 consecutive 16x16 blocks in serializer order.  Row pass:
-// thread (block, row) loads the row's 48 interleaved bytes once (3 x 128 bit), emits its 16 luma
-// bytes (kWithY) and the 16-point transform of each channel into a padded scratch tile; column
-// pass: thread (block, column) transforms the three channels' columns and writes the coefficients
-// at their place in the record.  Then one bulk store of the 8-record span.
+// CTA = 128 threads; a unit = 8 consecutive 16x16 blocks in serializer order, kIter16 consecutive
+// units per CTA.  Row pass: thread (block, row) holds the row's 48 interleaved bytes
+// (3 x 128 bit, loaded while the previous unit was transformed), emits its 16 luma bytes (kWithY) and
+// the 16-point transform of each channel into a padded, transposed scratch tile; column pass: thread
+// (block, column) transforms the three channels' columns and writes the coefficients at their place
+// in the record.  Then one bulk store of the 8-record span; its shared-memory read is awaited just
+// before the next unit's first record word is written.
+struct Unit16 {
+  uint32_t f, n0, n, px, py, bt;
+  bool active;
+};
+struct Div16 {  // ceil(2^64 / d): __umul64hi(n, m) == n / d for every 32-bit n
+  uint64_t m_chunks, m_nbx;
+};
+
 template <bool kWithY>
 __global__ void __launch_bounds__(128)
 dct16x16_stream_kernel(const DctParams p, const uint32_t nbx, const uint32_t nby_stream,
-                       const uint32_t nby_total, const YOut yo) {
-  __shared__ __align__(128) uint32_t stage[kUnit16 * kRecWords16];
-  __shared__ float tmp[2 * kTmp16Buf];
-  const uint32_t t = threadIdx.x, b = t >> 4, r = t & 15u;
+                       const uint32_t nby_total, const YOut yo, const uint32_t total_units,
+                       const uint32_t units_per_cta, const Div16 dv) {
+  __shared__ __align__(128) uint32_t stage[2 * kStageHalf16];
+  __shared__ __align__(16) float tmp[kTmp16Buf];
+  const uint32_t t = threadIdx.x, b = (t >> 5) + ((t >> 2) & 4u), r = t & 15u;
   const uint32_t per_frame = nbx * nby_total, per_stream = nbx * nby_stream;
   const uint32_t chunks_per_frame = (per_frame + kUnit16 - 1u) / kUnit16;
-  const uint32_t f = blockIdx.x / chunks_per_frame;
-  const uint32_t n0 = (blockIdx.x % chunks_per_frame) * kUnit16;
-  const uint32_t n = n0 + b;
-  const bool active = n < per_frame;
-  const uint32_t tbx = active ? n % nbx : 0u, tby = active ? n / nbx : 0u;
-  const uint32_t px = tbx * 16u, py = tby * 16u;
-
-  uint32_t raw[12];
-  {
-    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
-    if (active && py + r < p.h) {  // whole rows below the frame are the zero padding
-      const uint4* q = reinterpret_cast<const uint4*>(p.bgr + (((uint64_t)f * p.h + py + r) * p.w + px) * 3u);
-      v0 = __ldg(q); v1 = __ldg(q + 1); v2 = __ldg(q + 2);
+  auto locate = [&](const uint32_t u) {
+    Unit16 q;
+    q.f = chunks_per_frame > 1u ? (uint32_t)__umul64hi(u, dv.m_chunks) : u;
+    q.n0 = (u - q.f * chunks_per_frame) * kUnit16;
+    q.n = q.n0 + b;
+    q.active = q.n < per_frame;
+    const uint32_t tby = !q.active ? 0u : (nbx > 1u ? (uint32_t)__umul64hi(q.n, dv.m_nbx) : q.n);
+    const uint32_t tbx = q.active ? q.n - tby * nbx : 0u;
+    q.px = tbx * 16u;
+    q.py = tby * 16u;
+    q.bt = 0u;
+    if (r == 0 && p.block_types && q.n < per_stream)
+      q.bt = __ldg(p.block_types + (uint64_t)q.f * p.mv_field_w * p.mv_field_h +
+                   (q.py / p.mv_block_h) * p.mv_field_w + q.px / p.mv_block_w);
+    return q;
+  };
+  auto fetch = [&](const Unit16& q, uint4& v0, uint4& v1, uint4& v2) {
+    v0 = make_uint4(0, 0, 0, 0); v1 = v0; v2 = v0;
+    if (q.active && q.py + r < p.h) {  // whole rows below the frame are the zero padding
+      const uint4* g = reinterpret_cast<const uint4*>(p.bgr + (((uint64_t)q.f * p.h + q.py + r) * p.w + q.px) * 3u);
+      v0 = __ldg(g); v1 = __ldg(g + 1); v2 = __ldg(g + 2);
     }
-    raw[0] = v0.x; raw[1] = v0.y; raw[2] = v0.z; raw[3] = v0.w;
-    raw[4] = v1.x; raw[5] = v1.y; raw[6] = v1.z; raw[7] = v1.w;
-    raw[8] = v2.x; raw[9] = v2.y; raw[10] = v2.z; raw[11] = v2.w;
-  }
-  if (kWithY && active) {
-    const uint32_t lo[6] = {raw[0], raw[1], raw[2], raw[3], raw[4], raw[5]};
-    const uint32_t hi[6] = {raw[6], raw[7], raw[8], raw[9], raw[10], raw[11]};
-    const uint2 y0 = luma_row8(lo), y1 = luma_row8(hi);
-    uint8_t* yrow = yo.l0 + (uint64_t)(yo.first_slot + f) * yo.slot_bytes + (uint64_t)(py + r) * yo.pitch + px;
-    *reinterpret_cast<uint4*>(yrow) = make_uint4(y0.x, y0.y, y1.x, y1.y);
-  }
-  if (n0 >= per_stream) return;  // CTA-uniform: padded block rows carry no record
-
-  uint32_t* rec = stage + b * kRecWords16;
-  if (r == 0) {
-    uint32_t bt = 0;
-    if (p.block_types && n < per_stream)
-      bt = __ldg(p.block_types + (uint64_t)f * p.mv_field_w * p.mv_field_h +
-                 (py / p.mv_block_h) * p.mv_field_w + px / p.mv_block_w);
-    rec[0] = bt;
-  }
-  // channel c: row pass (thread = row r of block b) into scratch buffer c & 1, barrier, column pass
-  // (thread = column r of block b) into the record.  One barrier per channel is enough: whoever
-  // writes buffer c & 1 again (channel c + 2) has passed the barrier of channel c + 1, which every
-  // thread reaches only after its column pass of channel c.  The row is shifted down one byte per
-  // channel so that one code path (channel at byte 3j) serves B, G and R.
+  };
+  uint32_t u = blockIdx.x * units_per_cta;
+  const uint32_t u_end = min(u + units_per_cta, total_units);
+  Unit16 nxt = locate(u);
+  uint4 v0, v1, v2;
+  fetch(nxt, v0, v1, v2);
+  bool pending = false;  // a bulk store may still be reading `stage`
+  uint32_t* rec = stage + (b & 3u) * kRecWords16 + (b >> 2) * kStageHalf16;
+  float* buf = tmp + b * kTmp16Blk;
 #pragma unroll 1
-  for (int c = 0; c < 3; ++c) {
-    float* buf = tmp + (c & 1) * kTmp16Buf + b * kTmp16Blk;
-    {
-      float x[16], X[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = byte_to_magic(raw[(3 * j) >> 2], (3 * j) & 3);
-      dct16(x, X, 524288.0f);  // 8 sums of two magic floats: 8 * 2^16
-      float* trow = buf + r * 17u;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) trow[k] = X[k];
-#pragma unroll
-      for (int k = 0; k < 11; ++k) raw[k] = __funnelshift_r(raw[k], raw[k + 1], 8);
-      raw[11] >>= 8;
+  for (; u < u_end; ++u) {
+    const Unit16 q = nxt;
+    uint32_t raw[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+    if (u + 1 < u_end) {
+      nxt = locate(u + 1);
+      fetch(nxt, v0, v1, v2);
     }
-    __syncthreads();
-    {
-      const float* tcol = buf + r;
-      float x[16], X[16];
+    if (kWithY && q.active) {
+      const uint32_t lo[6] = {raw[0], raw[1], raw[2], raw[3], raw[4], raw[5]};
+      const uint32_t hi[6] = {raw[6], raw[7], raw[8], raw[9], raw[10], raw[11]};
+      const uint2 y0 = luma_row8(lo), y1 = luma_row8(hi);
+      uint8_t* yrow = yo.l0 + (uint64_t)(yo.first_slot + q.f) * yo.slot_bytes + (uint64_t)(q.py + r) * yo.pitch + q.px;
+      *reinterpret_cast<uint4*>(yrow) = make_uint4(y0.x, y0.y, y1.x, y1.y);
+    }
+    if (q.n0 >= per_stream) continue;  // CTA-uniform: padded block rows carry no record
+
+    // channel c: row pass (thread = row r of block b) into the scratch tile, barrier, column pass
+    // (thread = column r of block b) into the record, barrier (the barrier of the store after the
+    // last channel).  The row is shifted down one byte per channel so that one code path (channel
+    // at byte 3j) serves B, G and R.
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      {
+        float x[16], X[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = tcol[j * 17];
-      dct16(x, X, 0.f);
-      uint32_t* o = rec + 1 + c * 256 + r;
+        for (int j = 0; j < 16; ++j) x[j] = byte_to_magic(raw[(3 * j) >> 2], (3 * j) & 3);
+        dct16(x, X, 524288.0f);  // 8 sums of two magic floats: 8 * 2^16
 #pragma unroll
-      for (int k = 0; k < 16; ++k) o[k * 16] = __float_as_uint(X[k]);
+        for (int k = 0; k < 16; ++k) buf[k * kTmp16Pitch + r] = X[k];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) raw[k] = __funnelshift_r(raw[k], raw[k + 1], 8);
+        raw[11] >>= 8;
+      }
+      if (c == 0 && pending && t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncthreads();
+      if (c == 0 && r == 0) rec[0] = q.bt;
+      {
+        const float4* tcol = reinterpret_cast<const float4*>(buf + r * kTmp16Pitch);
+        const float4 a0 = tcol[0], a1 = tcol[1], a2 = tcol[2], a3 = tcol[3];
+        const float x[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
+                             a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+        float X[16];
+        dct16(x, X, 0.f);
+        uint32_t* o = rec + 1 + c * 256 + r;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) o[k * 16] = __float_as_uint(X[k]);
+      }
+      if (c < 2) __syncthreads();
+    }
+    const uint32_t n_act = min((uint32_t)kUnit16, per_stream - q.n0);
+    const uint32_t bytes0 = min(n_act, 4u) * kRecWords16 * 4u, bytes1 = (n_act - min(n_act, 4u)) * kRecWords16 * 4u;
+    uint8_t* dst = p.stream + (uint64_t)q.f * p.frame_stream_bytes + (uint64_t)q.n0 * (kRecWords16 * 4u);
+    if (((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) && (((bytes0 | bytes1) & 15u) == 0)) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (t == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes0) : "memory");
+        if (bytes1)
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       :: "l"(dst + bytes0), "r"((uint32_t)__cvta_generic_to_shared(stage + kStageHalf16)), "r"(bytes1)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      pending = true;
+    } else {
+      __syncthreads();
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+      for (uint32_t k = t; k < bytes0 / 4u; k += 128u) d32[k] = stage[k];
+      for (uint32_t k = t; k < bytes1 / 4u; k += 128u) d32[bytes0 / 4u + k] = stage[kStageHalf16 + k];
     }
   }
-  const uint32_t n_act = min((uint32_t)kUnit16, per_stream - n0);
-  store_span(stage, p.stream + (uint64_t)f * p.frame_stream_bytes + (uint64_t)n0 * (kRecWords16 * 4u),
-             n_act * kRecWords16 * 4u);
+  if (pending && t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the read
 }
 
 // 4-point orthonormal DCT-II
@@ -805,8 +859,13 @@ cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* nl) {
       static const char* env_pad = getenv("SVC_DCT_SMEM_PAD");
       const size_t pad = env_pad ? (size_t)atoi(env_pad) : 0;
       if (tb == 16) {
-        if (with_y) dct16x16_stream_kernel<true><<<(uint32_t)units, 128, 0, st>>>(p, nbx, nby, nby_total, yo);
-        else dct16x16_stream_kernel<false><<<(uint32_t)units, 128, 0, st>>>(p, nbx, nby, nby_total, yo);
+        static const char* env_it = getenv("SVC_DCT16_ITER");  // experiment hook: units per CTA
+        const uint32_t upc = env_it && atoi(env_it) > 0 ? (uint32_t)atoi(env_it) : (uint32_t)kIter16;
+        const uint32_t grid = (uint32_t)((units + upc - 1) / upc);
+        auto magic64 = [](uint32_t d) { return d > 1u ? ~0ull / d + 1ull : 0ull; };  // ceil(2^64 / d)
+        const Div16 dv{magic64((nbx * nby_total + kUnit16 - 1) / kUnit16), magic64(nbx)};
+        if (with_y) dct16x16_stream_kernel<true><<<grid, 128, 0, st>>>(p, nbx, nby, nby_total, yo, (uint32_t)units, upc, dv);
+        else dct16x16_stream_kernel<false><<<grid, 128, 0, st>>>(p, nbx, nby, nby_total, yo, (uint32_t)units, upc, dv);
       } else if (tb == 4) {
         if (with_y) dct4x4_stream_kernel<true><<<(uint32_t)units, kUnit4, 0, st>>>(p, nbx, nby, nby_total, yo);
         else dct4x4_stream_kernel<false><<<(uint32_t)units, kUnit4, 0, st>>>(p, nbx, nby, nby_total, yo);
