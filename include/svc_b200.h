@@ -206,7 +206,7 @@ int svc_session_synchronize(svc_session* s);
 #define SVC_STAGE_Y_PYRAMID 1 /* K1: frames -> pyramid slots 1..n */
 #define SVC_STAGE_HBMA 2      /* K2: slots i,i+1 -> mv/mad of frame i */
 #define SVC_STAGE_DCT_STREAM 3 /* K3: frames -> stream records (+ level-0 luma of slots 1..n
-                                  when the fused path applies: 8x8 blocks, W == padded W) */
+                                  when the fused path applies: square 8x8, 16x16 or 4x4 blocks, W == padded W) */
 #define SVC_STAGE_PYR_DOWN 4   /* K1b: level 0 of slots 1..n -> levels 1.. */
 int svc_session_run_stage(svc_session* s, int stage,
                           const uint8_t* d_frames_bgr, uint32_t n_frames,
@@ -239,7 +239,7 @@ int svc_gaze_rect(uint32_t gaze_x, uint32_t gaze_y, uint32_t max_gaze_rect_w,
  * NULL), background step for block type 0, foreground step otherwise (DecoderConfig,
  * libs/decoder.hpp:12-17; defaults 1 / 640, apps/decoder.cpp:20-25).  out_bgr: padded_h x
  * padded_w x 3 interleaved float -- the `upscaled_frame` before the division by 255 and
- * the resize.  8x8 transform blocks only. */
+ * the resize.  Square 8x8, 16x16 and 4x4 transform blocks. */
 int svc_decode_frame_blocks(const uint8_t* frame_records, uint32_t padded_w, uint32_t padded_h,
                             uint32_t tbw, uint32_t tbh, uint32_t fg_quant_step,
                             uint32_t bg_quant_step, const svc_rect* gaze, float* out_bgr);

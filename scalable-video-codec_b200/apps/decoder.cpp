@@ -78,8 +78,8 @@ int main(int argc, char** argv) {
   if (!read_all(in, hdr, 32)) { std::fprintf(stderr, "failed to read the stream header\n"); return EXIT_FAILURE; }
   svc_stream_layout lay{};
   CHECK(svc_stream_layout_from_header(hdr, &lay));
-  if (lay.tbw != 8 || lay.tbh != 8 || lay.channels != 3) {
-    std::fprintf(stderr, "svc_decoder: only 8x8 transform blocks of 3 channels are supported\n");
+  if (lay.tbw != lay.tbh || (lay.tbw != 8 && lay.tbw != 16 && lay.tbw != 4) || lay.channels != 3) {
+    std::fprintf(stderr, "svc_decoder: only 8x8, 16x16 and 4x4 transform blocks of 3 channels are supported\n");
     return EXIT_FAILURE;
   }
   const uint32_t pw = lay.padded_w, ph = lay.padded_h, w = lay.frame_w, h = lay.frame_h;

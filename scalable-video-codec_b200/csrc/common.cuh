@@ -94,9 +94,10 @@ cudaError_t prepare_dct_kernels();
 
 // ---- decoder block path: dequantise + 8x8 IDCT + merge ------------------------------
 struct DecodeParams {
-  const uint8_t* records;        // n_frames x frame_record_bytes (772-byte records, raster order)
+  const uint8_t* records;        // n_frames x frame_record_bytes (records of 4 + 12 tb^2 bytes, raster order)
   uint64_t frame_record_bytes;
-  uint32_t pw, ph;               // padded frame (multiples of 8)
+  uint32_t pw, ph;               // padded frame (multiples of the transform block)
+  uint32_t tb;                   // square transform block: 8 (0 = 8), 16 or 4
   uint32_t n_frames;
   uint32_t fg_q, bg_q;
   uint32_t has_gaze, gaze_x, gaze_y, gaze_w, gaze_h;

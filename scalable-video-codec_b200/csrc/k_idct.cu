@@ -140,12 +140,226 @@ idct8x8_decode_kernel(const DecodeParams p) {
   }
 }
 
+// ---- 4x4 and 16x16 transform blocks (streams of the fused dct4x4 / dct16x16 kernels) ----------
+
+// x = C^T X for the orthonormal 4-point DCT-II
+__device__ __forceinline__ void idct4(float& x0, float& x1, float& x2, float& x3) {
+  constexpr float a = 0.6532814824381883f, b = 0.27059805007309856f;  // sqrt(1/2) cos(pi/8), cos(3 pi/8)
+  const float p = 0.5f * (x0 + x2), q = 0.5f * (x0 - x2);
+  const float o0 = fmaf(a, x1, b * x3), o1 = fmaf(b, x1, -a * x3);
+  x0 = p + o0; x3 = p - o0;
+  x1 = q + o1; x2 = q - o1;
+}
+
+__device__ __forceinline__ float dequant(const uint32_t w, const float q) {
+  return __fmul_rn(roundf(__fdiv_rn(__uint_as_float(w), q)), q);  // libs/decoder.cpp:140-142
+}
+
+__device__ __forceinline__ bool in_gaze(const DecodeParams& p, const uint32_t x0, const uint32_t y0) {
+  return p.has_gaze && x0 >= p.gaze_x && x0 < p.gaze_x + p.gaze_w && y0 >= p.gaze_y && y0 < p.gaze_y + p.gaze_h;
+}
+
+// records -> shared memory: one TMA bulk copy per part on `bar` (phase 0), or a cooperative copy
+// when the span is not 16-byte aligned.  All threads call it and return with the data visible.
+__device__ __forceinline__ void fetch_records(uint32_t* dst0, const uint8_t* src, const uint32_t bytes0,
+                                              uint32_t* dst1, const uint32_t bytes1, uint64_t* bar) {
+  const bool bulk_ok = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && (((bytes0 | bytes1) & 15u) == 0);
+  if (bulk_ok) {
+    const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes0 + bytes1)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(dst0)), "l"(src), "r"(bytes0), "r"(bar_addr) : "memory");
+      if (bytes1)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(dst1)), "l"(src + bytes0), "r"(bytes1), "r"(bar_addr)
+                     : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar_addr), "r"(0u) : "memory");
+    }
+  } else {
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+    for (uint32_t k = threadIdx.x; k < bytes0 / 4u; k += blockDim.x) dst0[k] = __ldg(s32 + k);
+    for (uint32_t k = threadIdx.x; k < bytes1 / 4u; k += blockDim.x) dst1[k] = __ldg(s32 + bytes0 / 4u + k);
+    __syncthreads();
+  }
+}
+
+constexpr int kRecW4 = 49;               // words per 4x4 record
+constexpr int kUnitD4 = 128;             // records (lanes) per CTA
+constexpr int kOutBlk4 = 13;             // words per block per output row in smem (12 + 1 pad)
+constexpr int kOutRow4 = kUnitD4 * kOutBlk4;
+
+// One lane = one 4x4 block, three channels; the record buffer becomes the pixel tile.
+__global__ void __launch_bounds__(kUnitD4)
+idct4x4_decode_kernel(const DecodeParams p) {
+  __shared__ __align__(128) uint32_t stage[4 * kOutRow4];  // 26.6 KB >= 128 records (25.1 KB)
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t t = threadIdx.x;
+  const uint32_t nbx = p.pw / 4u, nby = p.ph / 4u;
+  const uint32_t chunks_x = (nbx + kUnitD4 - 1u) / kUnitD4;
+  uint32_t u = blockIdx.x;
+  const uint32_t cxi = u % chunks_x; u /= chunks_x;
+  const uint32_t by = u % nby, f = u / nby;
+  const uint32_t bx0 = cxi * kUnitD4, n_act = min((uint32_t)kUnitD4, nbx - bx0);
+  const uint8_t* src = p.records + (uint64_t)f * p.frame_record_bytes + ((uint64_t)by * nbx + bx0) * (kRecW4 * 4u);
+  fetch_records(stage, src, n_act * kRecW4 * 4u, stage, 0u, &bar);
+  float v[3][4][4];
+  const bool active = t < n_act;
+  if (active) {
+    const uint32_t* rec = stage + t * kRecW4;  // 49 lane + const: conflict free
+    const float q = (float)(in_gaze(p, (bx0 + t) * 4u, by * 4u) ? 1u : (rec[0] == 0u ? p.bg_q : p.fg_q));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[c][r][j] = dequant(rec[1 + c * 16 + r * 4 + j], q);
+        idct4(v[c][r][0], v[c][r][1], v[c][r][2], v[c][r][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) idct4(v[c][0][j], v[c][1][j], v[c][2][j], v[c][3][j]);
+    }
+  }
+  __syncthreads();  // every lane has consumed its record
+  if (active) {
+    uint32_t* o = stage + t * kOutBlk4;  // [row][block * 13 + px * 3 + channel]
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[r * kOutRow4 + j * 3 + c] = __float_as_uint(v[c][r][j]);
+  }
+  __syncthreads();
+  float* out = p.out + ((uint64_t)f * p.ph + (uint64_t)by * 4u) * p.pw * 3u + (uint64_t)bx0 * 12u;
+  const uint32_t vec_per_row = n_act * 3u;
+  for (uint32_t k = t; k < 4u * vec_per_row; k += kUnitD4) {
+    const uint32_t r = k / vec_per_row, i = k - r * vec_per_row;
+    const uint32_t b = i / 3u, q4 = i - b * 3u;
+    const uint32_t* s = stage + r * kOutRow4 + b * kOutBlk4 + q4 * 4u;
+    *reinterpret_cast<float4*>(out + (uint64_t)r * p.pw * 3u + (uint64_t)i * 4u) =
+        make_float4(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]), __uint_as_float(s[3]));
+  }
+}
+
+// 16-point inverse: x_i = e_i + o_i, x_{15-i} = e_i - o_i with e = IDCT8(X_even) / sqrt 2 and
+// o_i = sum_m sqrt(1/8) cos(pi (2i+1)(2m+1) / 32) X[2m+1] (transpose of the forward split of k_dct.cu).
+__device__ __forceinline__ constexpr float dct16_odd_factor(int i, int m) {
+  constexpr float K[8] = {0.35185093438159565f, 0.33832950029358816f, 0.31180625324666783f,
+                          0.2733004667504394f,  0.2242918965856591f,  0.1666639146194367f,
+                          0.10263113188058934f, 0.034654292299772925f};
+  int q = ((2 * i + 1) * (2 * m + 1)) % 64;
+  if (q > 32) q = 64 - q;
+  const bool neg = q > 16;
+  if (neg) q = 32 - q;
+  return neg ? -K[(q - 1) / 2] : K[(q - 1) / 2];
+}
+
+__device__ __forceinline__ void idct16(const float (&X)[16], float (&x)[16]) {
+  constexpr float k = 0.70710678118654752440f;
+  const float p = (SVC_C4 * k) * (X[0] + X[8]), q = (SVC_C4 * k) * (X[0] - X[8]);
+  const float r = fmaf(SVC_B2 * k, X[4], (SVC_B6 * k) * X[12]), s = fmaf(SVC_B6 * k, X[4], -(SVC_B2 * k) * X[12]);
+  const float e0 = p + r, e3 = p - r, e1 = q + s, e2 = q - s;
+  const float o0 = fmaf(SVC_A * k, X[2], fmaf(SVC_B * k, X[6], fmaf(SVC_C * k, X[10], (SVC_D * k) * X[14])));
+  const float o1 = fmaf(SVC_B * k, X[2], fmaf(-SVC_D * k, X[6], fmaf(-SVC_A * k, X[10], -(SVC_C * k) * X[14])));
+  const float o2 = fmaf(SVC_C * k, X[2], fmaf(-SVC_A * k, X[6], fmaf(SVC_D * k, X[10], (SVC_B * k) * X[14])));
+  const float o3 = fmaf(SVC_D * k, X[2], fmaf(-SVC_C * k, X[6], fmaf(SVC_B * k, X[10], -(SVC_A * k) * X[14])));
+  const float e[8] = {e0 + o0, e1 + o1, e2 + o2, e3 + o3, e3 - o3, e2 - o2, e1 - o1, e0 - o0};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float o = dct16_odd_factor(i, 0) * X[1];
+#pragma unroll
+    for (int m = 1; m < 8; ++m) o = fmaf(dct16_odd_factor(i, m), X[2 * m + 1], o);
+    x[i] = e[i] + o;
+    x[15 - i] = e[i] - o;
+  }
+}
+
+constexpr int kRecW16 = 769;                     // words per 16x16 record
+constexpr int kUnitD16 = 8;                      // records per CTA
+constexpr int kStageHalfD16 = 4 * kRecW16 + 12;  // blocks w and w + 4 of a warp sit 16 banks apart
+constexpr int kTmpPitchD16 = 20, kTmpBlkD16 = 16 * kTmpPitchD16 + 4;
+
+// Mirror image of dct16x16_stream_kernel: 128 threads own 8 consecutive records of a block row.
+// Per channel: thread (block, column) dequantises and inverse-transforms its column into a
+// transposed scratch tile, barrier, thread (block, row) inverse-transforms its row; the three
+// channels of a row are interleaved in registers and leave as 12 x 128-bit stores (192 contiguous
+// bytes per thread).
+__global__ void __launch_bounds__(128)
+idct16x16_decode_kernel(const DecodeParams p) {
+  __shared__ __align__(128) uint32_t stage[2 * kStageHalfD16];
+  __shared__ __align__(16) float tmp[kUnitD16 * kTmpBlkD16];
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t t = threadIdx.x, b = (t >> 5) + ((t >> 2) & 4u), r = t & 15u;
+  const uint32_t nbx = p.pw / 16u, nby = p.ph / 16u;
+  const uint32_t chunks_x = (nbx + kUnitD16 - 1u) / kUnitD16;
+  uint32_t u = blockIdx.x;
+  const uint32_t cxi = u % chunks_x; u /= chunks_x;
+  const uint32_t by = u % nby, f = u / nby;
+  const uint32_t bx0 = cxi * kUnitD16, n_act = min((uint32_t)kUnitD16, nbx - bx0);
+  const uint8_t* src = p.records + (uint64_t)f * p.frame_record_bytes + ((uint64_t)by * nbx + bx0) * (kRecW16 * 4u);
+  const uint32_t n0 = min(n_act, 4u);
+  fetch_records(stage, src, n0 * kRecW16 * 4u, stage + kStageHalfD16, (n_act - n0) * kRecW16 * 4u, &bar);
+  const bool active = b < n_act;
+  const uint32_t* rec = stage + (b & 3u) * kRecW16 + (b >> 2) * kStageHalfD16;
+  float* buf = tmp + b * kTmpBlkD16;
+  const float q = !active ? 1.f : (float)(in_gaze(p, (bx0 + b) * 16u, by * 16u) ? 1u : (rec[0] == 0u ? p.bg_q : p.fg_q));
+  float px[48];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    {
+      float X[16], x[16];
+#pragma unroll
+      for (int ky = 0; ky < 16; ++ky) X[ky] = active ? dequant(rec[1 + c * 256 + ky * 16 + r], q) : 0.f;
+      idct16(X, x);
+#pragma unroll
+      for (int y = 0; y < 16; ++y) buf[y * kTmpPitchD16 + r] = x[y];
+    }
+    __syncthreads();
+    {
+      const float4* trow = reinterpret_cast<const float4*>(buf + r * kTmpPitchD16);
+      const float4 a0 = trow[0], a1 = trow[1], a2 = trow[2], a3 = trow[3];
+      const float X[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
+                           a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+      float x[16];
+      idct16(X, x);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) px[j * 3 + c] = x[j];
+    }
+    if (c < 2) __syncthreads();
+  }
+  if (active) {
+    float4* o = reinterpret_cast<float4*>(p.out + (((uint64_t)f * p.ph + (uint64_t)by * 16u + r) * p.pw +
+                                                   (uint64_t)(bx0 + b) * 16u) * 3u);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) o[k] = make_float4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+  }
+}
+
 cudaError_t launch_decode(const DecodeParams& p, cudaStream_t st) {
   if (p.n_frames == 0) return cudaSuccess;
-  const uint32_t nbx = p.pw / 8u, nby = p.ph / 8u;
-  const uint64_t ctas = (uint64_t)((nbx + 31u) / 32u) * nby * p.n_frames;
+  const uint32_t tb = p.tb ? p.tb : 8u;
+  const uint32_t unit = tb == 8u ? 32u : (tb == 16u ? (uint32_t)kUnitD16 : (uint32_t)kUnitD4);
+  const uint32_t nbx = p.pw / tb, nby = p.ph / tb;
+  const uint64_t ctas = (uint64_t)((nbx + unit - 1u) / unit) * nby * p.n_frames;
   if (ctas > 0x7fffffffull) return cudaErrorInvalidValue;
-  idct8x8_decode_kernel<<<(uint32_t)ctas, 96, 0, st>>>(p);
+  if (tb == 8u) idct8x8_decode_kernel<<<(uint32_t)ctas, 96, 0, st>>>(p);
+  else if (tb == 16u) idct16x16_decode_kernel<<<(uint32_t)ctas, 128, 0, st>>>(p);
+  else if (tb == 4u) idct4x4_decode_kernel<<<(uint32_t)ctas, kUnitD4, 0, st>>>(p);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

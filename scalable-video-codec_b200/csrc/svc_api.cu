@@ -439,9 +439,10 @@ static int check_decode_args(uint32_t pw, uint32_t ph, uint32_t tbw, uint32_t tb
                              uint32_t bg_q) {
   if (fg_q == 0) return fail(SVC_ERR_INVALID_ARG, "invalid foreground quantization step: must be > 0");
   if (bg_q == 0) return fail(SVC_ERR_INVALID_ARG, "invalid background quantization step: must be > 0");
-  if (tbw != 8 || tbh != 8)
-    return fail(SVC_ERR_UNSUPPORTED, "the decoder block path supports 8x8 transform blocks only");
-  if (!pw || !ph || pw % 8 || ph % 8) return fail(SVC_ERR_INVALID_ARG, "padded dimensions must be multiples of 8");
+  if (tbw != tbh || (tbw != 8 && tbw != 16 && tbw != 4))
+    return fail(SVC_ERR_UNSUPPORTED, "the decoder block path supports 8x8, 16x16 and 4x4 transform blocks only");
+  if (!pw || !ph || pw % tbw || ph % tbh)
+    return fail(SVC_ERR_INVALID_ARG, "padded dimensions must be multiples of the transform block");
   if (pw > 32768 || ph > 32768) return fail(SVC_ERR_UNSUPPORTED, "frame too large");
   return SVC_OK;
 }
@@ -459,8 +460,9 @@ int svc_decode_frames_device(int device, void* cuda_stream, const uint8_t* d_rec
   if (rc) return rc;
   DecodeParams p{};
   p.records = d_records;
-  p.frame_record_bytes = (uint64_t)(padded_w / 8) * (padded_h / 8) * 772u;
+  p.frame_record_bytes = (uint64_t)(padded_w / tbw) * (padded_h / tbh) * (4u + 12u * tbw * tbh);
   p.pw = padded_w; p.ph = padded_h;
+  p.tb = tbw;
   p.n_frames = n_frames;
   p.fg_q = fg_quant_step; p.bg_q = bg_quant_step;
   if (gaze) { p.has_gaze = 1; p.gaze_x = gaze->x; p.gaze_y = gaze->y; p.gaze_w = gaze->w; p.gaze_h = gaze->h; }
@@ -477,7 +479,7 @@ int svc_decode_frame_blocks(const uint8_t* frame_records, uint32_t padded_w, uin
   if (rc) return rc;
   rc = prepare_device(g_device);
   if (rc) return rc;
-  const size_t in_bytes = (size_t)(padded_w / 8) * (padded_h / 8) * 772u;
+  const size_t in_bytes = (size_t)(padded_w / tbw) * (padded_h / tbh) * (4u + 12u * tbw * tbh);
   const size_t out_bytes = (size_t)padded_w * padded_h * 3 * sizeof(float);
   DevBuf in, out;
   CU(in.alloc(in_bytes));

@@ -282,11 +282,11 @@ def decode_frame_blocks(frame_records, padded_w, padded_h, fg_quant_step=1, bg_q
 
 
 def decode_frames_device(device, cuda_stream, d_records, n_frames, padded_w, padded_h, d_out,
-                         fg_quant_step=1, bg_quant_step=640, gaze=None):
+                         fg_quant_step=1, bg_quant_step=640, gaze=None, tb=8):
     g = C.byref(_Rect(*gaze)) if gaze is not None else None
     _check(lib().svc_decode_frames_device(C.c_int(device), C.c_void_p(cuda_stream or None),
                                           C.c_void_p(_addr(d_records)), C.c_uint32(n_frames),
-                                          C.c_uint32(padded_w), C.c_uint32(padded_h), C.c_uint32(8), C.c_uint32(8),
+                                          C.c_uint32(padded_w), C.c_uint32(padded_h), C.c_uint32(tb), C.c_uint32(tb),
                                           C.c_uint32(fg_quant_step), C.c_uint32(bg_quant_step), g,
                                           C.c_void_p(_addr(d_out))))
 

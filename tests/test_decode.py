@@ -40,8 +40,11 @@ def test_decode_argument_validation(svc):
         svc.decode_frame_blocks(rec, 16, 16, bg_quant_step=0)
     assert "background quantization step" in str(e.value)
     with pytest.raises(svc.SvcError) as e:
-        svc.decode_frame_blocks(rec, 16, 16, tbw=4, tbh=4)
+        svc.decode_frame_blocks(rec, 16, 16, tbw=8, tbh=4)
     assert e.value.code == 3
+    with pytest.raises(svc.SvcError) as e:
+        svc.decode_frame_blocks(rec, 24, 16, tbw=16, tbh=16)  # 24 is not a multiple of 16
+    assert e.value.code == 1
 
 
 @pytest.mark.gpu
@@ -94,3 +97,42 @@ def test_gpu_encode_decode_round_trip(gpu):
     # coarse background quantisation: still the same picture within the quantisation error
     dec = gpu.decode_frame_blocks(st, w, h, fg_quant_step=1, bg_quant_step=16)
     assert np.abs(dec - f[1].astype(np.float32)).mean() < 8.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tb", [4, 16])
+@pytest.mark.parametrize("pw,ph", [(1920, 1088), (272, 48), (16, 16), (80, 32), (2064, 32)])
+@pytest.mark.parametrize("fg,bg,with_gaze", [(1, 640, False), (3, 29, True)])
+def test_gpu_decode_square_blocks_vs_oracle(gpu, oracle, tb, pw, ph, fg, bg, with_gaze):
+    """16x16 and 4x4 records (the streams of the fused dct16x16 / dct4x4 kernels) through
+    idct16x16_decode_kernel / idct4x4_decode_kernel against the oracle's ParseBlock + DecodeBlock."""
+    rng = np.random.default_rng(pw + ph + fg + tb)
+    n, a = (pw // tb) * (ph // tb), tb * tb
+    rec = np.empty((n, 1 + 3 * a), np.uint32)
+    rec[:, 0] = rng.integers(0, 3, n)
+    coef = (rng.standard_normal((n, 3 * a)) * 300).astype(np.float32)
+    coef[:, ::a] = rng.uniform(0, 255 * tb, (n, 3)).astype(np.float32)  # DC terms
+    rec[:, 1:] = coef.view(np.uint32)
+    gaze = (pw // 4 // tb * tb, 0, min(64, pw), min(48, ph)) if with_gaze else None
+    got = gpu.decode_frame_blocks(rec.view(np.uint8).ravel(), pw, ph, fg, bg, gaze, tbw=tb, tbh=tb)
+    rows = 32 if pw * ph > 1000 * 1000 else ph   # the oracle on the first block rows of a large frame
+    exp = oracle.decode_frame_blocks(rec[: (pw // tb) * (rows // tb)].view(np.uint8).ravel(), pw, rows, tb, tb,
+                                     fg_q=fg, bg_q=bg, gaze=gaze)
+    assert np.abs(got[:rows] - exp).max() <= IDCT_TOL * (2 if tb == 16 else 1)
+    if rows < ph:
+        tail = rec[-(pw // tb) * (32 // tb):]
+        gz = None if gaze is None else (gaze[0], 0, 0, 0)
+        exp = oracle.decode_frame_blocks(tail.view(np.uint8).ravel(), pw, 32, tb, tb, fg_q=fg, bg_q=bg, gaze=gz)
+        assert np.abs(got[-32:] - exp).max() <= IDCT_TOL * (2 if tb == 16 else 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tb", [4, 16])
+def test_gpu_encode_decode_round_trip_square_blocks(gpu, tb):
+    from svc_b200.synth import SyntheticSequence
+    w, h = 320, 176
+    f = SyntheticSequence(w, h, 2, seed=5 + tb).frames()
+    st = gpu.encode_frame_stream(f[1], w, h, tb, tb)
+    dec = gpu.decode_frame_blocks(st, w, h, fg_quant_step=1, bg_quant_step=1, tbw=tb, tbh=tb)
+    err = np.abs(dec - f[1].astype(np.float32))
+    assert err.max() <= 0.5 * tb + 0.5 and err.mean() < 0.4

@@ -165,14 +165,15 @@ def test_decoder_app_validates_like_the_reference(oracle):
     hdr = oracle.header(3, 1000, 600, 1008, 608).tobytes()  # 1000 -> 1008: horizontal padding
     r = run(["-"], hdr)
     assert r.returncode != 0 and b"not decodable" in r.stderr
-    hdr = oracle.header(3, 64, 64, 64, 64, tbw=4, tbh=4).tobytes()
+    hdr = oracle.header(3, 64, 64, 64, 64, tbw=8, tbh=4).tobytes()
     r = run(["-"], hdr)
     assert r.returncode != 0 and b"8x8" in r.stderr
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("w,h,gaze", [(320, 176, None), (320, 180, (100, 60)), (1920, 1080, (960, 1070))])
-def test_encoder_app_piped_into_decoder_app(gpu, oracle, tmp_path, w, h, gaze):
+@pytest.mark.parametrize("w,h,gaze,tb", [(320, 176, None, 8), (320, 180, (100, 60), 8), (1920, 1080, (960, 1070), 8),
+                                         (320, 180, (100, 60), 16), (320, 172, None, 4)])
+def test_encoder_app_piped_into_decoder_app(gpu, oracle, tmp_path, w, h, gaze, tb):
     """svc_encoder | svc_decoder: every decoded frame equals the oracle's ParseBlock + DecodeBlock
     (libs/decoder.cpp:102-149) of the same records, rounded to 8 bits; at 1080p / 180 rows the encoder
     writes fewer block rows than the padded frame holds and the rest stays black."""
@@ -185,7 +186,8 @@ def test_encoder_app_piped_into_decoder_app(gpu, oracle, tmp_path, w, h, gaze):
     raw = tmp_path / "in.bgr"
     raw.write_bytes(frames.tobytes())
     r = subprocess.run([ENC, "--width", str(w), "--height", str(h), "--batch", "3", "--verbose", "0",
-                        "--seed", "3", str(raw)], capture_output=True, timeout=300)
+                        "--seed", "3", "--transform-block-w", str(tb), "--transform-block-h", str(tb), str(raw)],
+                       capture_output=True, timeout=300)
     assert r.returncode == 0, r.stderr
     stream = r.stdout
     fg, bg = 2, 24
@@ -197,15 +199,15 @@ def test_encoder_app_piped_into_decoder_app(gpu, oracle, tmp_path, w, h, gaze):
     assert d.returncode == 0, d.stderr
     pw, ph = oracle.padded_dim(w, 16, 4), oracle.padded_dim(h, 16, 4)
     out = np.frombuffer(d.stdout, np.uint8).reshape(n - 1, ph, pw, 3)
-    fb = oracle.serialized_frame_bytes(w, h)
-    rows = (h + 7) // 8 * 8  # block rows the encoder wrote
+    fb = oracle.serialized_frame_bytes(w, h, tb, tb)
+    rows = (h + tb - 1) // tb * tb  # block rows the encoder wrote
     gz = oracle.gaze_rect(gaze[0], gaze[1], 64, 64, w, h, pw, ph) if gaze else None
     if gz is not None and gz[1] + gz[3] > rows:  # the oracle decodes the written rows only
         gz = (gz[0], gz[1], gz[2], max(0, rows - gz[1]))
     step = 1 if w * h < 500 * 500 else n - 2   # the oracle's per-block loop is slow at 1080p
     for t in range(0, n - 1, step):
         rec = np.frombuffer(stream, np.uint8, fb, 32 + t * fb)
-        exp = oracle.decode_frame_blocks(rec, pw, rows, fg_q=fg, bg_q=bg, gaze=gz)
+        exp = oracle.decode_frame_blocks(rec, pw, rows, tb, tb, fg_q=fg, bg_q=bg, gaze=gz)
         exp8 = np.clip(np.rint(exp), 0, 255)
         got = out[t, :rows].astype(np.float32)
         # a float error <= 1e-3 can flip the 8-bit rounding only next to .5: allow those, nothing else
