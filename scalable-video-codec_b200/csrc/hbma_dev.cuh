@@ -52,5 +52,8 @@ inline bool encode_box(CUtensorMap* m, const uint8_t* base, uint32_t w, uint32_t
 struct HbmaParams;
 // (*extra_launches += launches beyond the first, for the level-synchronous path)
 bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int* extra_launches);
+// hbma_tile_kernel (k_hbma.cu) over the three coarsest levels of a 5-level pyramid (r = 3, 4): vectors
+// and MADs of level 2 land in p.mv / p.mad for the refinement launches of k_hbma_pool.cu
+cudaError_t launch_tile_upper3(const HbmaParams& p, cudaStream_t st);
 
 }  // namespace svc

@@ -759,6 +759,24 @@ static cudaError_t launch_tile(const HbmaParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// Five levels with r = 3, 4: the reach at level 0 (r * 31 pixels) does not fit a tile, the reach at
+// level 2 (r * 7) does.  The three coarsest levels run here as a 3-level pyramid with 4x4 base blocks
+// (levels 2, 3, 4 of the caller's layout); k_hbma_pool.cu refines levels 1 and 0 from p.mv / p.mad.
+cudaError_t launch_tile_upper3(const HbmaParams& p, cudaStream_t st) {
+  if (p.lay.levels != 5 || p.bw != 16 || p.bh != 16 || !p.mv || !p.mad) return cudaErrorInvalidValue;
+  if (p.n_frames > 65535 || (p.mvh + 3) / 4 > 65535) return cudaErrorInvalidValue;
+  HbmaParams q = p;
+  q.lay.levels = 3;
+  for (int l = 0; l < 3; ++l) {
+    q.lay.w[l] = p.lay.w[l + 2]; q.lay.h[l] = p.lay.h[l + 2];
+    q.lay.pitch[l] = p.lay.pitch[l + 2]; q.lay.off[l] = p.lay.off[l + 2];
+  }
+  q.bw = q.bh = 4;
+  if (p.r == 3) return launch_tile<3, 3, 4>(q, st);
+  if (p.r == 4) return launch_tile<3, 4, 4>(q, st);
+  return cudaErrorInvalidValue;
+}
+
 // (levels, r) pairs with a tiled instantiation; everything else takes the generic kernel
 static bool try_launch_tile(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
   if (p.n_frames > 65535 || (p.mvh + 3) / 4 > 65535) return false;

@@ -1073,6 +1073,16 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int
   const uint32_t L = p.lay.levels, r = p.r;
   // r <= 4: hbma_tile_kernel, or (5 levels, r = 3, 4: the reach does not fit a tile) the warp-per-block
   // window kernel of k_hbma.cu, which measures faster than per-level launches on such small windows
+  static const bool no_hybrid = getenv("SVC_HBMA_NO_HYBRID") != nullptr;  // experiment hook
+  if (!off && !no_hybrid && p.bw == 16 && p.bh == 16 && L == 5 && (r == 3 || r == 4) && p.mv && p.mad &&
+      p.n_frames <= 65535 && (uint64_t)p.mvw * p.mvh * p.n_frames <= 0x7fffffffull) {
+    // tile kernel over levels 4..2, then one refinement launch per remaining level
+    *err = launch_tile_upper3(p, st);
+    if (*err == cudaSuccess) *err = launch_refine<8, 7, 9, 128, 4, 8>(p, 1, st);
+    if (*err == cudaSuccess) *err = launch_refine<8, 7, 9, 128, 4, 16>(p, 0, st);
+    if (extra_launches) *extra_launches += 2;
+    return true;
+  }
   if (off || p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > (L == 1 ? 112u : 64u)) return false;
   if ((uint64_t)p.mvw * p.mvh * p.n_frames > 0x7fffffffull) return false;
   static const bool no_levels = getenv("SVC_HBMA_NO_LEVELS") != nullptr;  // experiment hook

@@ -96,7 +96,9 @@ def test_hbma_vs_oracle_generic(gpu, oracle, L, bw, bh, R):
 
 
 @pytest.mark.parametrize("L,R", [(4, 8), (4, 16), (4, 24), (4, 32), (3, 4), (3, 8), (3, 12), (3, 16),
-                                 (5, 16), (5, 32), (2, 2), (2, 4), (2, 6), (2, 8)])
+                                 (5, 16), (5, 32), (2, 2), (2, 4), (2, 6), (2, 8),
+                                 # 5 levels, r = 3, 4: tile kernel over levels 4..2 + refinement launches
+                                 (5, 48), (5, 55), (5, 64), (5, 79)])
 @pytest.mark.parametrize("w,h", [(352, 208), (176, 80)])
 def test_hbma_tiled_path_vs_oracle(gpu, oracle, L, R, w, h):
     """16x16 blocks with top-level range r = R >> (L-1) <= 4: the TMA-staged tiled kernel
@@ -402,7 +404,7 @@ def test_session_4k_geometry(gpu, oracle):
         assert np.abs(got - exp_blocks).max() <= DCT_TOL
 
 
-@pytest.mark.parametrize("R,L", [(8, 4), (24, 3), (40, 1)])
+@pytest.mark.parametrize("R,L", [(8, 4), (24, 3), (40, 1), (64, 5)])
 def test_device_work_counters_match_oracle(gpu, oracle, R, L):
     w, h, n = 176, 112, 3
     frames = SyntheticSequence(w, h, n, seed=R).frames()
