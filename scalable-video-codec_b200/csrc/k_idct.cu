@@ -292,15 +292,18 @@ constexpr int kRecW16 = 769;                     // words per 16x16 record
 constexpr int kUnitD16 = 8;                      // records per CTA
 constexpr int kStageHalfD16 = 4 * kRecW16 + 12;  // blocks w and w + 4 of a warp sit 16 banks apart
 constexpr int kTmpPitchD16 = 20, kTmpBlkD16 = 16 * kTmpPitchD16 + 4;
+constexpr int kPixPitchD16 = 49;                 // pixel tile: 48 floats per block row + 1
+constexpr int kStageD16 = kUnitD16 * 16 * kPixPitchD16 + 16;  // >= 2 * kStageHalfD16
 
 // Mirror image of dct16x16_stream_kernel: 128 threads own 8 consecutive records of a block row.
 // Per channel: thread (block, column) dequantises and inverse-transforms its column into a
 // transposed scratch tile, barrier, thread (block, row) inverse-transforms its row; the three
-// channels of a row are interleaved in registers and leave as 12 x 128-bit stores (192 contiguous
-// bytes per thread).
+// channels of a row are interleaved in registers, exchanged through the (then dead) record buffer
+// and leave as contiguous 128-bit stores of whole tile rows.
 __global__ void __launch_bounds__(128)
 idct16x16_decode_kernel(const DecodeParams p) {
-  __shared__ __align__(128) uint32_t stage[2 * kStageHalfD16];
+  static_assert(kStageD16 >= 2 * kStageHalfD16, "pixel tile must cover the records");
+  __shared__ __align__(128) uint32_t stage[kStageD16];
   __shared__ __align__(16) float tmp[kUnitD16 * kTmpBlkD16];
   __shared__ __align__(8) uint64_t bar;
   const uint32_t t = threadIdx.x, b = (t >> 5) + ((t >> 2) & 4u), r = t & 15u;
@@ -339,13 +342,26 @@ idct16x16_decode_kernel(const DecodeParams p) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) px[j * 3 + c] = x[j];
     }
-    if (c < 2) __syncthreads();
+    __syncthreads();
   }
-  if (active) {
-    float4* o = reinterpret_cast<float4*>(p.out + (((uint64_t)f * p.ph + (uint64_t)by * 16u + r) * p.pw +
-                                                   (uint64_t)(bx0 + b) * 16u) * 3u);
+  // The records are consumed (the barrier after the last column pass): the buffer becomes the pixel
+  // tile, [block][row] rows of 48 floats at pitch 49 (+16 words for blocks 4..7: conflict free), so
+  // that every output row of the unit (8 blocks x 192 B) leaves as contiguous 128-bit stores.
+  uint32_t* tile = stage;
+  {
+    uint32_t* o = tile + (b * 16u + r) * kPixPitchD16 + (b >> 2) * 16u;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) o[k] = make_float4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+    for (int k = 0; k < 48; ++k) o[k] = __float_as_uint(px[k]);
+  }
+  __syncthreads();
+  float* out = p.out + ((uint64_t)f * p.ph + (uint64_t)by * 16u) * p.pw * 3u + (uint64_t)bx0 * 48u;
+  const uint32_t vec_per_row = n_act * 12u;
+  for (uint32_t k = t; k < 16u * vec_per_row; k += 128u) {
+    const uint32_t y = k / vec_per_row, i = k - y * vec_per_row;
+    const uint32_t bb = i / 12u, k4 = i - bb * 12u;
+    const uint32_t* sp = tile + (bb * 16u + y) * kPixPitchD16 + (bb >> 2) * 16u + k4 * 4u;
+    *reinterpret_cast<float4*>(out + (uint64_t)y * p.pw * 3u + (uint64_t)i * 4u) =
+        make_float4(__uint_as_float(sp[0]), __uint_as_float(sp[1]), __uint_as_float(sp[2]), __uint_as_float(sp[3]));
   }
 }
 
