@@ -270,6 +270,29 @@ def test_dct_known_answers(gpu):
                 assert np.abs(d[c] - o).max() <= DCT_TOL, (key, c)
 
 
+def test_dct_known_answers_through_the_fused_stream_kernels(gpu):
+    """The cv2.dct known-answer blocks (tests/golden/dct_kat.npz) laid side by side in one frame and
+    sent through the fused 8x8 / 4x4 / 16x16 stream kernels: record k must hold cv2's coefficients of
+    block k in all three channels."""
+    g = load_golden("dct_kat.npz")
+    for key, tb in (("8", 8), ("4", 4), ("16", 16)):
+        blocks, outs = g["b" + key], g["o" + key]
+        row = np.concatenate([b.astype(np.uint8) for b in blocks], axis=1)
+        while row.shape[1] % 16:  # frame width: a multiple of 16 (the fused 16x16 kernel loads 16-byte aligned rows)
+            row = np.concatenate([row, row], axis=1)
+        frame = np.tile(row, (16 // tb, 1))  # 16 rows: one row of motion blocks
+        bgr = np.ascontiguousarray(np.repeat(frame[..., None], 3, axis=2))
+        nbx = bgr.shape[1] // tb
+        st = gpu.encode_frame_stream(bgr, bgr.shape[1], 16, tb, tb)
+        rec = st.view(np.uint32).reshape(-1, 1 + 3 * tb * tb)
+        assert rec.shape[0] == nbx * (16 // tb)
+        for k in range(rec.shape[0]):
+            exp = outs[(k % nbx) % len(blocks)]
+            for c in range(3):
+                got = rec[k, 1 + c * tb * tb: 1 + (c + 1) * tb * tb].view(np.float32).reshape(tb, tb)
+                assert np.abs(got - exp).max() <= DCT_TOL, (key, k, c)
+
+
 @pytest.mark.parametrize("w,h,tbw,tbh", [(1920, 1080, 8, 8), (104, 56, 8, 8), (96, 48, 4, 4),
                                          (64, 64, 16, 16), (80, 48, 8, 4), (48, 80, 2, 16)])
 def test_dct_planar_vs_oracle(gpu, oracle, w, h, tbw, tbh):
