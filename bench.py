@@ -54,7 +54,8 @@ def parse():
 
 
 def workload_name(a):
-    return (f"C2 synthetic {a.width}x{a.height} 8-bit BGR, {a.frames} input frames "
+    cfg = {(960, 540): "C1", (1920, 1080): "C2", (3840, 2160): "C4"}.get((a.width, a.height), "custom")  # BASELINE.json configs
+    return (f"{cfg} synthetic {a.width}x{a.height} 8-bit BGR, {a.frames} input frames "
             f"({a.frames - 1} encoded) per GPU, 16x16 MV blocks, R={a.search_range}, "
             f"L={a.levels}, 8x8 DCT, 772-byte stream records")
 
