@@ -91,7 +91,10 @@ def test_random_wide_range_session(gpu, oracle, cfg):
 
 @pytest.mark.parametrize("w,h,mb,L,tb,n,batch", [(320, 180, 16, 4, 16, 5, 3), (320, 176, 16, 4, 4, 4, 2),
                                                   (64, 40, 16, 3, 16, 3, 1), (200, 90, 8, 3, 4, 4, 3),
-                                                  (1920, 1080, 16, 4, 16, 3, 2), (960, 540, 16, 4, 4, 3, 2)])
+                                                  (1920, 1080, 16, 4, 16, 3, 2), (960, 540, 16, 4, 4, 3, 2),
+                                                  # padded block rows that carry luma but no record (32x32 MV blocks)
+                                                  (64, 40, 32, 3, 16, 3, 2), (192, 72, 32, 2, 16, 4, 3),
+                                                  (96, 36, 32, 3, 4, 3, 1)])
 def test_session_fused_square_transform_blocks(gpu, oracle, w, h, mb, L, tb, n, batch):
     """Frames without horizontal padding and 16x16 / 4x4 transform blocks: the fused stream kernels
     (records + level-0 luma in one pass) inside a session -- the motion field checks their luma."""
