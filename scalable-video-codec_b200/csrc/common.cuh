@@ -57,6 +57,9 @@ struct HbmaParams {
   float* mad;   // n_frames x mvh x mvw, may be null
   uint32_t n_frames;
   uint32_t force_generic;  // 1 = always take the universal kernel (tests)
+  // > 0: the search co-runs with another kernel (the session's motion stream next to K3): persistent
+  // small-footprint CTAs, this many per SM (default configuration only; 0 = one CTA per tile)
+  uint32_t corun_ctas_per_sm;
   // optional exact work counters: [0] += candidates, [1] += byte-absdiffs
   unsigned long long* counters;
 };

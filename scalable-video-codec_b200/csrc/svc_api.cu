@@ -582,7 +582,7 @@ bool needs_scratch(const svc_session* s) {
 // (join_motion) before anything that consumes motion vectors.
 int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, float* d_mv,
                         float* d_mad, uint8_t* d_stream, const uint32_t* d_bt,
-                        uint32_t* n_enc_out) {
+                        uint32_t* n_enc_out, bool k3_follows = false) {
   const uint32_t first_slot = s->have_prev ? 1u : 0u;
   const uint32_t n_enc = s->have_prev ? m : m - 1;
   const uint32_t cur = s->batch_idx & 1u;
@@ -662,6 +662,10 @@ int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, flo
     p.mv = reinterpret_cast<float2*>(d_mv);
     p.mad = d_mad;
     p.n_frames = n_enc;
+    // Experiment hook (read per launch; measured and rejected): persistent
+    // small-footprint search CTAs, this many per SM, co-resident with the next batch's K3.
+    const char* env_corun = getenv("SVC_HBMA_CORUN");
+    if (env_corun && k3_follows) p.corun_ctas_per_sm = (uint32_t)std::max(0, atoi(env_corun));
     CU(launch_hbma(p, s->s_aux, &nl));
   }
   CU(cudaEventRecord(s->ev_motion[cur], s->s_aux));
@@ -919,7 +923,7 @@ int svc_session_encode_device(svc_session* s, const uint8_t* d_frames, uint32_t 
         s, d_frames + (size_t)done_in * s->info.frame_in_bytes, m,
         d_mv ? d_mv + done_enc * mvn * 2 : nullptr, d_mad ? d_mad + done_enc * mvn : nullptr,
         d_stream ? d_stream + (size_t)done_enc * s->info.frame_stream_bytes : nullptr,
-        d_bt ? d_bt + done_enc * mvn : nullptr, &ne);
+        d_bt ? d_bt + done_enc * mvn : nullptr, &ne, d_stream != nullptr && done_in + m < n_frames);
     if (rc) return rc;
     done_in += m;
     done_enc += ne;

@@ -510,3 +510,30 @@ def test_stage_entry_points(gpu, oracle):
         for i in (1, 2):  # slot i+1 vs slot i  (slot 0 is the zero-initialised previous frame)
             emv, _ = oracle.hbma(pyr[i - 1], pyr[i], 8)
             assert np.array_equal(mv[i], emv)
+
+
+def test_session_corun_search_variant_is_bit_exact(gpu, oracle, monkeypatch):
+    """SVC_HBMA_CORUN (experiment hook, device-resident path): the persistent two-row tile kernel that
+    co-runs with the next batch's K3 must give the same vectors and MADs as the oracle (several
+    batches per call, the last one on the regular kernel)."""
+    monkeypatch.setenv("SVC_HBMA_CORUN", "3")
+    w, h, n = 352, 208, 9
+    frames = SyntheticSequence(w, h, n, seed=123).frames()
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, max_batch=3)) as s:
+        mvn = s.mv_field_w * s.mv_field_h
+        d_in = gpu.DeviceBuffer(0, frames.nbytes)
+        d_mv = gpu.DeviceBuffer(0, (n - 1) * mvn * 8)
+        d_mad = gpu.DeviceBuffer(0, (n - 1) * mvn * 4)
+        d_st = gpu.DeviceBuffer(0, (n - 1) * s.frame_stream_bytes)
+        d_in.upload(frames)
+        assert s.encode_device(d_in, n, d_mv, d_mad, d_st) == n - 1
+        s.synchronize()
+        mv = d_mv.download(np.float32, (n - 1, s.mv_field_h, s.mv_field_w, 2))
+        mad = d_mad.download(np.float32, (n - 1, s.mv_field_h, s.mv_field_w))
+        pw, ph = s.padded_w, s.padded_h
+        pyr = [oracle.y_pyramid(f, pw, ph, 4) for f in frames]
+        for i in range(1, n):
+            emv, emad = oracle.hbma(pyr[i - 1], pyr[i], 8)
+            assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad), i
+        for b in (d_in, d_mv, d_mad, d_st):
+            b.free()
