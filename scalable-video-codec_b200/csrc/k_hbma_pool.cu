@@ -1111,7 +1111,7 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int
   static const char* env_v = getenv("SVC_HBMA_POOL_VARIANT");  // tuning hook
   const int variant = env_v ? atoi(env_v) : 0;
   // <range class, blocks per CTA, candidate rows per item, threads, CTAs per SM>: measured best of
-  // several shapes per class on B200 (profiles/r01_sweep_hbma_v11.md)
+  // several shapes per class on B200 (profiles/r01_sweep_hbma_v12.md)
   static const bool no_tile = getenv("SVC_HBMA_NO_EBMA_TILE") != nullptr;  // experiment hook
   if (L == 1 && r > 32 && !no_tile) {
     // <range class, stripe width in candidate columns, candidate rows per item, threads, CTAs per SM>
