@@ -103,9 +103,43 @@ def make_decode_golden():
     np.savez_compressed(os.path.join(HERE, "decode_blocks.npz"), records=st, pw=pw, ph=ph, **outs)
 
 
+def make_decode_golden_square(tb):
+    """The same for 16x16 / 4x4 transform blocks (tests/golden/decode_blocks_tb{tb}.npz): cv2.dct
+    planes -> records -> quantise -> cv2.idct -> merge."""
+    rng = np.random.default_rng(770 + tb)
+    pw, ph = 144, 48  # 9 x 3 blocks of 16: a partial 8-record unit; 36 x 12 blocks of 4
+    f = rng.integers(0, 256, (ph, pw, 3)).astype(np.uint8)
+    planes = cv_dct_planes(f, pw, ph, tb, tb)
+    bt = rng.integers(0, 3, (ph // 16) * (pw // 16)).astype(np.uint32)
+    st = py_serialize(planes, bt, pw, ph, tb, tb, pw // 16, 16, 16)
+    a = tb * tb
+    rec = st.view(np.uint32).reshape(-1, 1 + 3 * a)
+    outs = {}
+    for name, fg, bg, gaze in (("a", 1, 640, None), ("b", 3, 40, (16, 16, 64, 16)), ("c", 5, 5, (0, 0, pw, ph))):
+        exp = np.zeros((ph, pw, 3), np.float32)
+        k = 0
+        for y in range(0, ph, tb):
+            for x in range(0, pw, tb):
+                t = rec[k, 0]
+                gazed = gaze is not None and gaze[0] <= x < gaze[0] + gaze[2] and gaze[1] <= y < gaze[1] + gaze[3]
+                q = np.float32(1 if gazed else (bg if t == 0 else fg))
+                for c in range(3):
+                    b = rec[k, 1 + a * c:1 + a * (c + 1)].view(np.float32).reshape(tb, tb) / q
+                    b = np.where(b >= 0, np.floor(b + np.float32(0.5)), np.ceil(b - np.float32(0.5))).astype(np.float32) * q
+                    exp[y:y + tb, x:x + tb, c] = cv2.idct(b)
+                k += 1
+        outs["out_" + name] = exp
+        outs["cfg_" + name] = np.array([fg, bg] + (list(gaze) if gaze else [0, 0, 0, 0]) + [int(gaze is not None)], np.int64)
+    np.savez_compressed(os.path.join(HERE, "decode_blocks_tb%d.npz" % tb), records=st, pw=pw, ph=ph, tb=tb, **outs)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "decode":
         make_decode_golden()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "decode_square":
+        make_decode_golden_square(16)
+        make_decode_golden_square(4)
         return
     assert O.have_ref(), "build oracle/_ref first: make -C oracle"
     rng = np.random.default_rng(20260101)

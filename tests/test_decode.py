@@ -23,6 +23,15 @@ def test_oracle_decode_matches_cv2_golden(oracle):
         assert np.abs(out - exp).max() <= IDCT_TOL
 
 
+@pytest.mark.parametrize("tb", [16, 4])
+def test_oracle_decode_square_blocks_matches_cv2_golden(oracle, tb):
+    """16x16 / 4x4 records: the oracle against cv2.idct (tests/golden/make_golden.py decode_square)."""
+    g = load_golden("decode_blocks_tb%d.npz" % tb)
+    for fg, bg, gaze, exp in _cases(g):
+        out = oracle.decode_frame_blocks(g["records"], int(g["pw"]), int(g["ph"]), tb, tb, fg_q=fg, bg_q=bg, gaze=gaze)
+        assert np.abs(out - exp).max() <= IDCT_TOL
+
+
 @pytest.mark.parametrize("args", [(100, 50, 64, 64, 960, 540, 960, 544), (5, 535, 64, 64, 960, 540, 960, 544),
                                   (0, 0, 64, 64, 1920, 1080, 1920, 1088), (1919, 1079, 64, 64, 1920, 1080, 1920, 1088),
                                   (500, 300, 31, 77, 1000, 600, 1008, 608)])
@@ -52,6 +61,15 @@ def test_gpu_decode_golden(gpu):
     g = load_golden("decode_blocks.npz")
     for fg, bg, gaze, exp in _cases(g):
         out = gpu.decode_frame_blocks(g["records"], int(g["pw"]), int(g["ph"]), fg, bg, gaze)
+        assert np.abs(out - exp).max() <= IDCT_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tb", [16, 4])
+def test_gpu_decode_square_blocks_golden(gpu, tb):
+    g = load_golden("decode_blocks_tb%d.npz" % tb)
+    for fg, bg, gaze, exp in _cases(g):
+        out = gpu.decode_frame_blocks(g["records"], int(g["pw"]), int(g["ph"]), fg, bg, gaze, tbw=tb, tbh=tb)
         assert np.abs(out - exp).max() <= IDCT_TOL
 
 
