@@ -291,21 +291,30 @@ dct8x8_stream_kernel(const DctParams p, const uint32_t nbx, const uint32_t nby_s
 // divides the 16x16 motion block).  Needs w == pw like the 8x8 kernel, so that the serializer's
 // unpadded row stride and swapped loop bounds (libs/encoder.cpp:257-262) coincide with the plane.
 
+// sqrt(1/8) cos(k pi / 16), k = 1..7 and 1/4 for the DC term: the 8-point factors times 1/sqrt(2),
+// rounded once from the exact value (a float product of two rounded factors is up to 2 ulp off,
+// and 0.35355339f * 0.70710678f is 0.24999998, which alone costs 5e-4 on a DC of 4080)
+#define SVC_H4 0.25f
+#define SVC_HA  0.3467599613305369f
+#define SVC_HB2 0.32664074121909414f
+#define SVC_HB  0.2939689006048397f
+#define SVC_HC  0.1964237395967756f
+#define SVC_HB6 0.13529902503654928f
+#define SVC_HD  0.06897484482073578f
 // 8-point transform of the even half of a 16-point one: every factor times 1/sqrt(2); `dc_off`
 // is what the DC sum carries when the inputs are magic floats (0 otherwise).
 __device__ __forceinline__ void dct8_half(const float (&s)[8], float (&o)[8], const float dc_off) {
-  constexpr float k = 0.70710678118654752440f;
   const float s0 = s[0] + s[7], s1 = s[1] + s[6], s2 = s[2] + s[5], s3 = s[3] + s[4];
   const float d0 = s[0] - s[7], d1 = s[1] - s[6], d2 = s[2] - s[5], d3 = s[3] - s[4];
   const float e0 = s0 + s3, e1 = s1 + s2, e2 = s0 - s3, e3 = s1 - s2;
-  o[0] = (SVC_C4 * k) * ((e0 + e1) - dc_off);
-  o[4] = (SVC_C4 * k) * (e0 - e1);
-  o[2] = fmaf(SVC_B2 * k, e2, (SVC_B6 * k) * e3);
-  o[6] = fmaf(SVC_B6 * k, e2, -(SVC_B2 * k) * e3);
-  o[1] = fmaf(SVC_A * k, d0, fmaf(SVC_B * k, d1, fmaf(SVC_C * k, d2, (SVC_D * k) * d3)));
-  o[3] = fmaf(SVC_B * k, d0, fmaf(-SVC_D * k, d1, fmaf(-SVC_A * k, d2, -(SVC_C * k) * d3)));
-  o[5] = fmaf(SVC_C * k, d0, fmaf(-SVC_A * k, d1, fmaf(SVC_D * k, d2, (SVC_B * k) * d3)));
-  o[7] = fmaf(SVC_D * k, d0, fmaf(-SVC_C * k, d1, fmaf(SVC_B * k, d2, -(SVC_A * k) * d3)));
+  o[0] = SVC_H4 * ((e0 + e1) - dc_off);
+  o[4] = SVC_H4 * (e0 - e1);
+  o[2] = fmaf(SVC_HB2, e2, SVC_HB6 * e3);
+  o[6] = fmaf(SVC_HB6, e2, -SVC_HB2 * e3);
+  o[1] = fmaf(SVC_HA, d0, fmaf(SVC_HB, d1, fmaf(SVC_HC, d2, SVC_HD * d3)));
+  o[3] = fmaf(SVC_HB, d0, fmaf(-SVC_HD, d1, fmaf(-SVC_HA, d2, -SVC_HC * d3)));
+  o[5] = fmaf(SVC_HC, d0, fmaf(-SVC_HA, d1, fmaf(SVC_HD, d2, SVC_HB * d3)));
+  o[7] = fmaf(SVC_HD, d0, fmaf(-SVC_HC, d1, fmaf(SVC_HB, d2, -SVC_HA * d3)));
 }
 
 // sqrt(2/16) cos(pi q / 32), q = 1, 3, .., 15

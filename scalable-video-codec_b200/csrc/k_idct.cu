@@ -255,6 +255,14 @@ idct4x4_decode_kernel(const DecodeParams p) {
   }
 }
 
+// sqrt(1/8) cos(k pi / 16), k = 1..7 and 1/4: the 8-point factors times 1/sqrt(2), rounded once (see k_dct.cu)
+#define SVC_H4 0.25f
+#define SVC_HA  0.3467599613305369f
+#define SVC_HB2 0.32664074121909414f
+#define SVC_HB  0.2939689006048397f
+#define SVC_HC  0.1964237395967756f
+#define SVC_HB6 0.13529902503654928f
+#define SVC_HD  0.06897484482073578f
 // 16-point inverse: x_i = e_i + o_i, x_{15-i} = e_i - o_i with e = IDCT8(X_even) / sqrt 2 and
 // o_i = sum_m sqrt(1/8) cos(pi (2i+1)(2m+1) / 32) X[2m+1] (transpose of the forward split of k_dct.cu).
 __device__ __forceinline__ constexpr float dct16_odd_factor(int i, int m) {
@@ -269,14 +277,13 @@ __device__ __forceinline__ constexpr float dct16_odd_factor(int i, int m) {
 }
 
 __device__ __forceinline__ void idct16(const float (&X)[16], float (&x)[16]) {
-  constexpr float k = 0.70710678118654752440f;
-  const float p = (SVC_C4 * k) * (X[0] + X[8]), q = (SVC_C4 * k) * (X[0] - X[8]);
-  const float r = fmaf(SVC_B2 * k, X[4], (SVC_B6 * k) * X[12]), s = fmaf(SVC_B6 * k, X[4], -(SVC_B2 * k) * X[12]);
+  const float p = SVC_H4 * (X[0] + X[8]), q = SVC_H4 * (X[0] - X[8]);
+  const float r = fmaf(SVC_HB2, X[4], SVC_HB6 * X[12]), s = fmaf(SVC_HB6, X[4], -SVC_HB2 * X[12]);
   const float e0 = p + r, e3 = p - r, e1 = q + s, e2 = q - s;
-  const float o0 = fmaf(SVC_A * k, X[2], fmaf(SVC_B * k, X[6], fmaf(SVC_C * k, X[10], (SVC_D * k) * X[14])));
-  const float o1 = fmaf(SVC_B * k, X[2], fmaf(-SVC_D * k, X[6], fmaf(-SVC_A * k, X[10], -(SVC_C * k) * X[14])));
-  const float o2 = fmaf(SVC_C * k, X[2], fmaf(-SVC_A * k, X[6], fmaf(SVC_D * k, X[10], (SVC_B * k) * X[14])));
-  const float o3 = fmaf(SVC_D * k, X[2], fmaf(-SVC_C * k, X[6], fmaf(SVC_B * k, X[10], -(SVC_A * k) * X[14])));
+  const float o0 = fmaf(SVC_HA, X[2], fmaf(SVC_HB, X[6], fmaf(SVC_HC, X[10], SVC_HD * X[14])));
+  const float o1 = fmaf(SVC_HB, X[2], fmaf(-SVC_HD, X[6], fmaf(-SVC_HA, X[10], -SVC_HC * X[14])));
+  const float o2 = fmaf(SVC_HC, X[2], fmaf(-SVC_HA, X[6], fmaf(SVC_HD, X[10], SVC_HB * X[14])));
+  const float o3 = fmaf(SVC_HD, X[2], fmaf(-SVC_HC, X[6], fmaf(SVC_HB, X[10], -SVC_HA * X[14])));
   const float e[8] = {e0 + o0, e1 + o1, e2 + o2, e3 + o3, e3 - o3, e2 - o2, e1 - o1, e0 - o0};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {

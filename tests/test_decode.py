@@ -136,12 +136,12 @@ def test_gpu_decode_square_blocks_vs_oracle(gpu, oracle, tb, pw, ph, fg, bg, wit
     rows = 32 if pw * ph > 1000 * 1000 else ph   # the oracle on the first block rows of a large frame
     exp = oracle.decode_frame_blocks(rec[: (pw // tb) * (rows // tb)].view(np.uint8).ravel(), pw, rows, tb, tb,
                                      fg_q=fg, bg_q=bg, gaze=gaze)
-    assert np.abs(got[:rows] - exp).max() <= IDCT_TOL * (2 if tb == 16 else 1)
+    assert np.abs(got[:rows] - exp).max() <= IDCT_TOL
     if rows < ph:
         tail = rec[-(pw // tb) * (32 // tb):]
         gz = None if gaze is None else (gaze[0], 0, 0, 0)
         exp = oracle.decode_frame_blocks(tail.view(np.uint8).ravel(), pw, 32, tb, tb, fg_q=fg, bg_q=bg, gaze=gz)
-        assert np.abs(got[-32:] - exp).max() <= IDCT_TOL * (2 if tb == 16 else 1)
+        assert np.abs(got[-32:] - exp).max() <= IDCT_TOL
 
 
 @pytest.mark.gpu
