@@ -34,19 +34,40 @@ namespace svc {
 #define SVC_B6 0.19134171618254488586f /* cos(6 pi/16) / 2 */
 #define SVC_D  0.09754516100806413392f /* cos(7 pi/16) / 2 */
 
+// sqrt(1/8) cos(k pi / 16), k = 1..7 and 1/4 for the DC term: the 8-point factors times 1/sqrt(2),
+// rounded once from the exact value (a float product of two rounded factors is up to 2 ulp off,
+// and 0.35355339f * 0.70710678f is 0.24999998, which alone costs 5e-4 on a DC of 4080)
+#define SVC_H4 0.25f
+#define SVC_HA  0.3467599613305369f
+#define SVC_HB2 0.32664074121909414f
+#define SVC_HB  0.2939689006048397f
+#define SVC_HC  0.1964237395967756f
+#define SVC_HB6 0.13529902503654928f
+#define SVC_HD  0.06897484482073578f
+// The 2-D 8x8 transform applies the row pass with every factor times sqrt(2) and the column pass with
+// every factor times 1/sqrt(2): the product is unchanged, but both DC factors (1/2 and 1/4) are exact,
+// which halves the worst-case error on bright blocks.  sqrt(1/2) cos(k pi / 16), k = 1..7:
+#define SVC_R4 0.5f
+#define SVC_RA  0.6935199226610738f
+#define SVC_RB2 0.6532814824381883f
+#define SVC_RB  0.5879378012096794f
+#define SVC_RC  0.3928474791935512f
+#define SVC_RB6 0.27059805007309856f
+#define SVC_RD  0.13794968964147156f
+
 __device__ __forceinline__ void dct8(float& x0, float& x1, float& x2, float& x3,
                                      float& x4, float& x5, float& x6, float& x7) {
   const float s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;
   const float d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;
   const float e0 = s0 + s3, e1 = s1 + s2, e2 = s0 - s3, e3 = s1 - s2;
-  x0 = SVC_C4 * (e0 + e1);
-  x4 = SVC_C4 * (e0 - e1);
-  x2 = fmaf(SVC_B2, e2, SVC_B6 * e3);
-  x6 = fmaf(SVC_B6, e2, -SVC_B2 * e3);
-  x1 = fmaf(SVC_A, d0, fmaf(SVC_B, d1, fmaf(SVC_C, d2, SVC_D * d3)));
-  x3 = fmaf(SVC_B, d0, fmaf(-SVC_D, d1, fmaf(-SVC_A, d2, -SVC_C * d3)));
-  x5 = fmaf(SVC_C, d0, fmaf(-SVC_A, d1, fmaf(SVC_D, d2, SVC_B * d3)));
-  x7 = fmaf(SVC_D, d0, fmaf(-SVC_C, d1, fmaf(SVC_B, d2, -SVC_A * d3)));
+  x0 = SVC_H4 * (e0 + e1);
+  x4 = SVC_H4 * (e0 - e1);
+  x2 = fmaf(SVC_HB2, e2, SVC_HB6 * e3);
+  x6 = fmaf(SVC_HB6, e2, -SVC_HB2 * e3);
+  x1 = fmaf(SVC_HA, d0, fmaf(SVC_HB, d1, fmaf(SVC_HC, d2, SVC_HD * d3)));
+  x3 = fmaf(SVC_HB, d0, fmaf(-SVC_HD, d1, fmaf(-SVC_HA, d2, -SVC_HC * d3)));
+  x5 = fmaf(SVC_HC, d0, fmaf(-SVC_HA, d1, fmaf(SVC_HD, d2, SVC_HB * d3)));
+  x7 = fmaf(SVC_HD, d0, fmaf(-SVC_HC, d1, fmaf(SVC_HB, d2, -SVC_HA * d3)));
 }
 
 // Row pass on "magic" floats.  A byte b placed in bits [15:8] of 0x47000000 is
@@ -63,14 +84,14 @@ __device__ __forceinline__ void dct8_magic(float& x0, float& x1, float& x2, floa
   const float s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;   // 2^16 + ..
   const float d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;   // exact
   const float e0 = s0 + s3, e1 = s1 + s2, e2 = s0 - s3, e3 = s1 - s2;
-  x0 = SVC_C4 * ((e0 + e1) - 262144.0f);
-  x4 = SVC_C4 * (e0 - e1);
-  x2 = fmaf(SVC_B2, e2, SVC_B6 * e3);
-  x6 = fmaf(SVC_B6, e2, -SVC_B2 * e3);
-  x1 = fmaf(SVC_A, d0, fmaf(SVC_B, d1, fmaf(SVC_C, d2, SVC_D * d3)));
-  x3 = fmaf(SVC_B, d0, fmaf(-SVC_D, d1, fmaf(-SVC_A, d2, -SVC_C * d3)));
-  x5 = fmaf(SVC_C, d0, fmaf(-SVC_A, d1, fmaf(SVC_D, d2, SVC_B * d3)));
-  x7 = fmaf(SVC_D, d0, fmaf(-SVC_C, d1, fmaf(SVC_B, d2, -SVC_A * d3)));
+  x0 = SVC_R4 * ((e0 + e1) - 262144.0f);
+  x4 = SVC_R4 * (e0 - e1);
+  x2 = fmaf(SVC_RB2, e2, SVC_RB6 * e3);
+  x6 = fmaf(SVC_RB6, e2, -SVC_RB2 * e3);
+  x1 = fmaf(SVC_RA, d0, fmaf(SVC_RB, d1, fmaf(SVC_RC, d2, SVC_RD * d3)));
+  x3 = fmaf(SVC_RB, d0, fmaf(-SVC_RD, d1, fmaf(-SVC_RA, d2, -SVC_RC * d3)));
+  x5 = fmaf(SVC_RC, d0, fmaf(-SVC_RA, d1, fmaf(SVC_RD, d2, SVC_RB * d3)));
+  x7 = fmaf(SVC_RD, d0, fmaf(-SVC_RC, d1, fmaf(SVC_RB, d2, -SVC_RA * d3)));
 }
 
 // 8x8 block of channel C out of 8 rows x 24 interleaved bytes -> 64 coefficients
@@ -291,16 +312,6 @@ dct8x8_stream_kernel(const DctParams p, const uint32_t nbx, const uint32_t nby_s
 // divides the 16x16 motion block).  Needs w == pw like the 8x8 kernel, so that the serializer's
 // unpadded row stride and swapped loop bounds (libs/encoder.cpp:257-262) coincide with the plane.
 
-// sqrt(1/8) cos(k pi / 16), k = 1..7 and 1/4 for the DC term: the 8-point factors times 1/sqrt(2),
-// rounded once from the exact value (a float product of two rounded factors is up to 2 ulp off,
-// and 0.35355339f * 0.70710678f is 0.24999998, which alone costs 5e-4 on a DC of 4080)
-#define SVC_H4 0.25f
-#define SVC_HA  0.3467599613305369f
-#define SVC_HB2 0.32664074121909414f
-#define SVC_HB  0.2939689006048397f
-#define SVC_HC  0.1964237395967756f
-#define SVC_HB6 0.13529902503654928f
-#define SVC_HD  0.06897484482073578f
 // 8-point transform of the even half of a 16-point one: every factor times 1/sqrt(2); `dc_off`
 // is what the DC sum carries when the inputs are magic floats (0 otherwise).
 __device__ __forceinline__ void dct8_half(const float (&s)[8], float (&o)[8], const float dc_off) {
