@@ -27,16 +27,39 @@ namespace svc {
 #define SVC_B6 0.19134171618254488586f
 #define SVC_D  0.09754516100806413392f
 
-// x = C^T X for the orthonormal 8-point DCT-II matrix C (even/odd split, 34 flops)
+// sqrt(1/8) cos(k pi / 16), k = 1..7 and 1/4: the 8-point factors times 1/sqrt(2), rounded once (see k_dct.cu)
+#define SVC_H4 0.25f
+#define SVC_HA  0.3467599613305369f
+#define SVC_HB2 0.32664074121909414f
+#define SVC_HB  0.2939689006048397f
+#define SVC_HC  0.1964237395967756f
+#define SVC_HB6 0.13529902503654928f
+#define SVC_HD  0.06897484482073578f
+// sqrt(1/2) cos(k pi / 16): the same factors times sqrt(2)
+#define SVC_R4 0.5f
+#define SVC_RA  0.6935199226610738f
+#define SVC_RB2 0.6532814824381883f
+#define SVC_RB  0.5879378012096794f
+#define SVC_RC  0.3928474791935512f
+#define SVC_RB6 0.27059805007309856f
+#define SVC_RD  0.13794968964147156f
+
+// x = C^T X for the orthonormal 8-point DCT-II matrix C (even/odd split, 34 flops).  The 2-D inverse
+// applies one pass with every factor times sqrt(2) (kUp) and the other with every factor times
+// 1/sqrt(2): the product is unchanged and both DC factors (1/2, 1/4) are exact, as in k_dct.cu.
+template <bool kUp>
 __device__ __forceinline__ void idct8(float& x0, float& x1, float& x2, float& x3,
                                       float& x4, float& x5, float& x6, float& x7) {
-  const float p = SVC_C4 * (x0 + x4), q = SVC_C4 * (x0 - x4);
-  const float r = fmaf(SVC_B2, x2, SVC_B6 * x6), s = fmaf(SVC_B6, x2, -SVC_B2 * x6);
+  constexpr float c4 = kUp ? SVC_R4 : SVC_H4, ca = kUp ? SVC_RA : SVC_HA, cb2 = kUp ? SVC_RB2 : SVC_HB2,
+                  cb = kUp ? SVC_RB : SVC_HB, cc = kUp ? SVC_RC : SVC_HC, cb6 = kUp ? SVC_RB6 : SVC_HB6,
+                  cd = kUp ? SVC_RD : SVC_HD;
+  const float p = c4 * (x0 + x4), q = c4 * (x0 - x4);
+  const float r = fmaf(cb2, x2, cb6 * x6), s = fmaf(cb6, x2, -cb2 * x6);
   const float e0 = p + r, e3 = p - r, e1 = q + s, e2 = q - s;
-  const float o0 = fmaf(SVC_A, x1, fmaf(SVC_B, x3, fmaf(SVC_C, x5, SVC_D * x7)));
-  const float o1 = fmaf(SVC_B, x1, fmaf(-SVC_D, x3, fmaf(-SVC_A, x5, -SVC_C * x7)));
-  const float o2 = fmaf(SVC_C, x1, fmaf(-SVC_A, x3, fmaf(SVC_D, x5, SVC_B * x7)));
-  const float o3 = fmaf(SVC_D, x1, fmaf(-SVC_C, x3, fmaf(SVC_B, x5, -SVC_A * x7)));
+  const float o0 = fmaf(ca, x1, fmaf(cb, x3, fmaf(cc, x5, cd * x7)));
+  const float o1 = fmaf(cb, x1, fmaf(-cd, x3, fmaf(-ca, x5, -cc * x7)));
+  const float o2 = fmaf(cc, x1, fmaf(-ca, x3, fmaf(cd, x5, cb * x7)));
+  const float o3 = fmaf(cd, x1, fmaf(-cc, x3, fmaf(cb, x5, -ca * x7)));
   x0 = e0 + o0; x7 = e0 - o0;
   x1 = e1 + o1; x6 = e1 - o1;
   x2 = e2 + o2; x5 = e2 - o2;
@@ -113,9 +136,9 @@ idct8x8_decode_kernel(const DecodeParams p) {
         v[r][j] = __fmul_rn(roundf(__fdiv_rn(cf, q)), q);  // libs/decoder.cpp:140-142
       }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) idct8(v[r][0], v[r][1], v[r][2], v[r][3], v[r][4], v[r][5], v[r][6], v[r][7]);
+    for (int r = 0; r < 8; ++r) idct8<true>(v[r][0], v[r][1], v[r][2], v[r][3], v[r][4], v[r][5], v[r][6], v[r][7]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) idct8(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+    for (int j = 0; j < 8; ++j) idct8<false>(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
   }
   __syncthreads();  // every warp has consumed the records: the buffer becomes the pixel tile
   if (active) {
@@ -255,14 +278,6 @@ idct4x4_decode_kernel(const DecodeParams p) {
   }
 }
 
-// sqrt(1/8) cos(k pi / 16), k = 1..7 and 1/4: the 8-point factors times 1/sqrt(2), rounded once (see k_dct.cu)
-#define SVC_H4 0.25f
-#define SVC_HA  0.3467599613305369f
-#define SVC_HB2 0.32664074121909414f
-#define SVC_HB  0.2939689006048397f
-#define SVC_HC  0.1964237395967756f
-#define SVC_HB6 0.13529902503654928f
-#define SVC_HD  0.06897484482073578f
 // 16-point inverse: x_i = e_i + o_i, x_{15-i} = e_i - o_i with e = IDCT8(X_even) / sqrt 2 and
 // o_i = sum_m sqrt(1/8) cos(pi (2i+1)(2m+1) / 32) X[2m+1] (transpose of the forward split of k_dct.cu).
 __device__ __forceinline__ constexpr float dct16_odd_factor(int i, int m) {
