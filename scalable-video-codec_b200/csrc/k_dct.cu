@@ -13,7 +13,10 @@
 //   * stages whole 772-byte records in shared memory in stream order and hands
 //     each warp's contiguous span to the TMA engine (cp.async.bulk shared ->
 //     global), so the record layout costs no scattered stores.
-// Generic path (any transform block up to 32x32): separable matrix form with
+// 16x16 and 4x4 transform blocks have their own fused stream kernels with the same contract
+// (dct16x16_stream_kernel: row pass / transposed scratch tile / column pass with an even-odd split
+// 16-point transform; dct4x4_stream_kernel: one lane per block).
+// Generic path (any other transform block up to 32x32, or W != padded W): separable matrix form with
 // the basis in constant memory, plus a gather kernel that reproduces the
 // reference serializer index arithmetic exactly (including its use of the
 // unpadded width as row stride, libs/encoder.cpp:257-262).

@@ -14,7 +14,8 @@
 // bank-conflict free at the 193-word record stride); the pixels are exchanged through
 // shared memory so that every output row of the tile leaves as contiguous 128-bit
 // stores (32 blocks x 8 px x 3 channels = 3 KB per row).  HBM-bound: 772 B in,
-// 768 B out per block.
+// 768 B out per block.  idct16x16_decode_kernel / idct4x4_decode_kernel (further down) are the
+// mirror images of dct16x16_stream_kernel / dct4x4_stream_kernel for 3076-byte and 196-byte records.
 #include "common.cuh"
 
 namespace svc {
