@@ -45,8 +45,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=100, help="max frames per kernel launch")
     ap.add_argument("--search-range", type=int, default=8)
     ap.add_argument("--levels", type=int, default=4)
-    ap.add_argument("--cpu-sample-frames", type=int, default=97,
-                    help="input frames in the CPU baseline sample")
+    ap.add_argument("--cpu-sample-frames", type=int, default=300,
+                    help="input frames in the CPU baseline sample (default: the whole 300-frame workload, about 25 core-seconds on 16 cores)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sad", action="store_true", help="skip the SAD-roofline side measurement (R=32/64, L=1)")
