@@ -45,8 +45,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=100, help="max frames per kernel launch")
     ap.add_argument("--search-range", type=int, default=8)
     ap.add_argument("--levels", type=int, default=4)
-    ap.add_argument("--cpu-sample-frames", type=int, default=300,
-                    help="input frames in the CPU baseline sample (default: the whole 300-frame workload, about 25 core-seconds on 16 cores)")
+    ap.add_argument("--cpu-sample-frames", type=int, default=0,
+                    help="input frames in the CPU baseline sample (default 0: the whole --frames workload, "
+                         "about 25 core-seconds for 300 frames of 1080p)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity check of the measured outputs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sad", action="store_true", help="skip the SAD-roofline side measurement (R=32/64, L=1)")
@@ -54,10 +56,34 @@ def parse():
 
 
 def workload_name(a):
-    cfg = {(960, 540): "C1", (1920, 1080): "C2", (3840, 2160): "C4"}.get((a.width, a.height), "custom")  # BASELINE.json configs
+    # BASELINE.json configs, keyed on what is actually run
+    if (a.width, a.height, a.frames) == (960, 540, 30):
+        cfg = "C1"
+    elif (a.width, a.height, a.frames) == (1920, 1080, 300):
+        cfg = "C2"
+    elif (a.width, a.height) == (3840, 2160) and a.frames * a.gpus == 600:
+        cfg = "C4"
+    else:
+        cfg = "custom"
     return (f"{cfg} synthetic {a.width}x{a.height} 8-bit BGR, {a.frames} input frames "
             f"({a.frames - 1} encoded) per GPU, 16x16 MV blocks, R={a.search_range}, "
             f"L={a.levels}, 8x8 DCT, 772-byte stream records")
+
+
+def config_dict(a):
+    """The `config` object of the JSON line: identical in both arms (`--impl ours|reference`)."""
+    fin = a.width * a.height * 3
+    fst = -(-a.width // 8) * -(-a.height // 8) * 772
+    return {"workload": workload_name(a), "frames_per_step_per_gpu": a.frames - 1,
+            "batch_frames_per_launch": a.batch,
+            "l2": "per-step working set (%.1f GB in + %.1f GB out per GPU) far exceeds the "
+                  "126 MB L2; no explicit flush" % (a.frames * fin / 1e9, (a.frames - 1) * fst / 1e9),
+            "sharding": "contiguous frame ranges, one overlap frame, no collective"}
+
+
+ORACLE_PIN = ("MV/MAD: unmodified reference libs/motion.cpp (oracle/_ref, SSE2 entry); Y/pyramid/DCT/"
+              "serializer: oracle/svc_oracle.c pinned to python cv2 4.13 fixtures (the reference names "
+              "OpenCV 3.4.*, libs/encoder.cpp is not buildable here)")
 
 
 def host_cores():
@@ -73,7 +99,8 @@ def cpu_hot_path_fps(a, frames, threads):
     Y pyramid (C port of the OpenCV calls) -> reference HBMA (compiled unmodified
     libs/motion.cpp, SSE2 entry, when it travelled; else the C port) -> per-block
     DCT + SerializeEncodedFrame (C port).  Frame-range sharded over `threads`
-    host threads (the reference itself computes on one thread)."""
+    host threads (the reference itself computes on one thread).
+    Returns (frames/s, seconds, description, per-stage busy ms per frame and core)."""
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import oracle as O
@@ -82,24 +109,43 @@ def cpu_hot_path_fps(a, frames, threads):
     pw, ph = O.padded_dim(w, 16, L), O.padded_dim(h, 16, L)
     use_ref = O.have_ref() and L == 4
     mvw = pw // 16
+    pc = time.perf_counter
 
     def work(lo, hi):  # encoded frames lo..hi-1 (anchor index), needs frame lo-1
+        t_y = t_m = t_d = 0.0
+        t0 = pc()
         prev = O.y_pyramid(frames[lo - 1], pw, ph, L)
+        t_y += pc() - t0
         for i in range(lo, hi):
+            t0 = pc()
             cur = O.y_pyramid(frames[i], pw, ph, L)
+            t1 = pc()
             O.hbma(prev, cur, R, impl="ref_sse2" if use_ref else "oracle")
+            t2 = pc()
             planes = O.dct_planar(frames[i], pw, ph)
             O.serialize_frame(planes, None, w, h, 8, 8, mvw, 16, 16)
+            t3 = pc()
+            t_y += t1 - t0
+            t_m += t2 - t1
+            t_d += t3 - t2
             prev = cur
+        return t_y, t_m, t_d
 
     from svc_b200.shard import shard_frame_ranges
     ranges = [r for r in shard_frame_ranges(n, threads) if r[3] > r[2]]
-    t0 = time.perf_counter()
+    t0 = pc()
     with ThreadPoolExecutor(max_workers=len(ranges)) as ex:
-        list(ex.map(lambda r: work(r[2], r[3]), ranges))
-    dt = time.perf_counter() - t0
-    return (n - 1) / dt, dt, ("reference libs/motion.cpp (SSE2 entry) + C port of the OpenCV stages"
-                              if use_ref else "C port (oracle/svc_oracle.c)")
+        parts = list(ex.map(lambda r: work(r[2], r[3]), ranges))
+    dt = pc() - t0
+    ne = n - 1
+    split = {"ypyr_ms": 1e3 * sum(p[0] for p in parts) / ne, "hbma_ms": 1e3 * sum(p[1] for p in parts) / ne,
+             "dct_serialize_ms": 1e3 * sum(p[2] for p in parts) / ne,
+             "note": "busy milliseconds per encoded frame on one core, summed over the shard threads: "
+                     "ypyr = C port of copyMakeBorder+cvtColor+extractChannel+buildPyramid, hbma = "
+                     + ("reference EstimateMotionHierarchical16x16Sse2" if use_ref else "C port of the HBMA")
+                     + ", dct_serialize = C port of the per-block DCT + SerializeEncodedFrame"}
+    return ne / dt, dt, ("reference libs/motion.cpp (SSE2 entry) + C port of the OpenCV stages"
+                         if use_ref else "C port (oracle/svc_oracle.c)"), split
 
 
 def run_reference(a):
@@ -108,28 +154,93 @@ def run_reference(a):
         return
     from svc_b200.synth import SyntheticSequence
     threads = host_cores()
-    n = max(2, a.cpu_sample_frames)
+    n = max(2, a.cpu_sample_frames or a.frames)
     frames = SyntheticSequence(a.width, a.height, n, seed=1234).frames()
     for _ in range(a.warmup):
         cpu_hot_path_fps(a, frames[: min(n, threads + 1)], threads)
-    t_tot, fps_list, what = 0.0, [], ""
+    t_tot, what, splits = 0.0, "", []
     for _ in range(a.steps):
-        fps, dt, what = cpu_hot_path_fps(a, frames, threads)
+        fps, dt, what, split = cpu_hot_path_fps(a, frames, threads)
         t_tot += dt
-        fps_list.append(fps)
+        splits.append(split)
     value = (n - 1) * a.steps / t_tot
     sample = f"{n} input frames ({n - 1} encoded) of the workload per step; {what}"
+    stage_split = {k: float(np.mean([sp[k] for sp in splits])) for k in ("ypyr_ms", "hbma_ms", "dct_serialize_ms")}
+    stage_split["note"] = splits[0]["note"] if splits else ""
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * t_tot / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "frames_per_step": n - 1},
+        "config": config_dict(a),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads,
-                         "kind": "port", "sample": sample},
+                         "kind": "port", "sample": sample, "stage_split": stage_split},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "oracle_pin": ORACLE_PIN,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- parity
+def check_parity(a, frames, outputs, pw, ph, threads, dct_frames=8):
+    """Compare the outputs of the measured workload with the checkers: EVERY motion field / MAD
+    field against the compiled reference (EstimateMotionHierarchical16x16Sse2, libs/motion.cpp:691-749;
+    the generic entry or the C port for other level counts), the records of `dct_frames` evenly
+    spaced frames against the oracle DCT + serializer (libs/encoder.cpp:323-339, 222-269).
+    frames: (n,h,w,3) input.  outputs: {name: (mv (n-1,mh,mw,2), mad (n-1,mh,mw), stream_of)} with
+    stream_of(k) -> record bytes of encoded frame k (0-based)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+    n, h, w, _ = frames.shape
+    L, R = a.levels, a.search_range
+    impl = "ref_sse2" if (O.have_ref() and L == 4) else ("ref" if O.have_ref() else "oracle")
+    mvw = pw // 16
+    ne = n - 1
+    bad = {name: [] for name in outputs}
+
+    def work(lo, hi):
+        prev = O.y_pyramid(frames[lo - 1], pw, ph, L)
+        for i in range(lo, hi):
+            cur = O.y_pyramid(frames[i], pw, ph, L)
+            emv, emad = O.hbma(prev, cur, R, impl=impl)
+            for name, (mv, mad, _) in outputs.items():
+                if not (np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad)):
+                    bad[name].append(i)
+            prev = cur
+
+    from svc_b200.shard import shard_frame_ranges
+    ranges = [r for r in shard_frame_ranges(n, max(1, threads)) if r[3] > r[2]]
+    with ThreadPoolExecutor(max_workers=len(ranges)) as ex:
+        list(ex.map(lambda r: work(r[2], r[3]), ranges))
+
+    picks = sorted({int(round(x)) for x in np.linspace(1, ne, min(dct_frames, ne))})
+
+    def dct_err(i):
+        exp = O.serialize_frame(O.dct_planar(frames[i], pw, ph), None, w, h, 8, 8, mvw, 16, 16).reshape(-1, 772)
+        ef = exp[:, 4:].copy().view(np.float32)
+        err, bt_ok = 0.0, True
+        for name, (_, _, stream_of) in outputs.items():
+            g = np.asarray(stream_of(i - 1)).reshape(-1, 772)
+            bt_ok &= bool(np.array_equal(exp[:, :4], g[:, :4]))
+            err = max(err, float(np.abs(ef - g[:, 4:].copy().view(np.float32)).max()))
+        return err, bt_ok
+
+    with ThreadPoolExecutor(max_workers=max(1, min(threads, len(picks)))) as ex:
+        errs = list(ex.map(dct_err, picks))
+    dct_max = max(e for e, _ in errs)
+    mv_ok = not any(bad.values())
+    res = {"mv_frames": ne, "mv_bit_exact": mv_ok, "mad_bit_exact": mv_ok,
+           "outputs_checked": sorted(outputs),
+           "mv_checker": {"ref_sse2": "reference EstimateMotionHierarchical16x16Sse2 (oracle/_ref), every frame",
+                          "ref": "reference EstimateMotionHierarchical (oracle/_ref), every frame",
+                          "oracle": "C port (oracle/svc_oracle.c), every frame"}[impl],
+           "dct_frames": len(picks), "dct_max_abs_err": dct_max, "dct_tolerance_abs": 1e-3,
+           "block_type_words_exact": all(ok for _, ok in errs), "oracle_pin": ORACLE_PIN}
+    if not mv_ok:
+        res["first_bad_frames"] = {k: sorted(v)[:8] for k, v in bad.items() if v}
+    res["ok"] = bool(mv_ok and dct_max <= 1e-3 and res["block_type_words_exact"])
+    return res
 
 
 # --------------------------------------------------------------------------- clocks
@@ -138,6 +249,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.segments = {}  # name -> [t0, t1] (perf_counter)
         self._stop = threading.Event()
         self._t = None
         try:
@@ -162,13 +274,12 @@ class ClockSampler:
                 util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
                 mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((mhz, util))
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                rs = [name for bit, name in names.items() if r & bit]
+                self.samples.append((mhz, util, time.perf_counter(), rs))
+                self.reasons.update(rs)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv:
@@ -182,9 +293,29 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                     "samples": 0}
-        mhz = [m for m, _ in self.samples]
-        return {"sm_mhz": float(np.median(mhz)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(mhz)}
+        mhz = [m[0] for m in self.samples]
+        out = {"sm_mhz": float(np.median(mhz)), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(mhz)}
+        per = {}
+        for name, (t0, t1) in self.segments.items():
+            seg = [m for m in self.samples if t0 <= m[2] <= t1]
+            if seg:
+                per[name] = {"sm_mhz": float(np.median([m[0] for m in seg])), "samples": len(seg),
+                             "reasons": sorted({r for m in seg for r in m[3]})}
+        if per:
+            out["per_stage"] = per
+        return out
+
+    def segment(self, name):
+        sampler = self
+
+        class _Seg:
+            def __enter__(self):
+                sampler.segments[name] = [time.perf_counter(), float("inf")]
+
+            def __exit__(self, *exc):
+                sampler.segments[name][1] = time.perf_counter()
+        return _Seg()
 
 
 def bind_to_gpu_numa_node(index):
@@ -290,11 +421,12 @@ def run_ours(a):
     clocks.start()
     l0 = sess.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(ts):
+    with clocks.segment("step"), torch.cuda.stream(ts):
         e0.record(ts)
         for _ in range(a.steps):
             step()
         e1.record(ts)
+        torch.cuda.synchronize()
     barrier()
     launches = sess.launch_count - l0
     ms_total = e0.elapsed_time(e1)
@@ -304,17 +436,28 @@ def run_ours(a):
     ms_step = float(t.item()) / a.steps
     value = world * n_enc / (ms_step * 1e-3)
 
+    # outputs of the LAST timed step, kept for the parity check (the stage timings below overwrite them)
+    par_out = {}
+    if not a.no_parity:
+        mh_, mw_ = sess.mv_field_h, sess.mv_field_w
+        ne_ = n_enc
+        picks_ = sorted({int(round(x)) - 1 for x in np.linspace(1, ne_, min(8, ne_))})
+        st_dev = {k: d_st[k * fst:(k + 1) * fst].cpu().numpy() for k in picks_}
+        par_out["device_resident"] = (d_mv.cpu().numpy().reshape(ne_, mh_, mw_, 2),
+                                      d_mad.cpu().numpy().reshape(ne_, mh_, mw_), st_dev.__getitem__)
+
     # ---------------- per-stage timing (dominant kernel roofline) -------------------
-    def time_stage(fn, reps=3):
+    def time_stage(fn, name, reps=40):
+        fn()  # untimed warm-up of this stage
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_launch = 0
-        with torch.cuda.stream(ts):
+        with clocks.segment(name), torch.cuda.stream(ts):
             s0.record(ts)
             for _ in range(reps):
                 n_launch += fn()
             s1.record(ts)
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
         return s0.elapsed_time(s1) / n_launch  # ms per launch(-group)
 
     B = a.batch
@@ -339,9 +482,9 @@ def run_ours(a):
 
     stages = {}
     if nb >= 1:
-        ms_dct = time_stage(stage_dct)
-        ms_pyr = time_stage(stage_pyr)
-        ms_hbma = max(time_stage(stage_pyr_hbma) - ms_pyr, 1e-6)
+        ms_dct = time_stage(stage_dct, "dct_stream_y")
+        ms_pyr = time_stage(stage_pyr, "pyr_down")
+        ms_hbma = max(time_stage(stage_pyr_hbma, "hbma") - ms_pyr, 1e-6)
         P = sess.padded_w * sess.padded_h
         fused_y = (W == sess.padded_w)                     # K3 also writes the level-0 luma
         dct_bytes = B * (fin + fst + (P if fused_y else 0))  # read BGR once, write records (+Y) once
@@ -356,20 +499,28 @@ def run_ours(a):
             "hbma": {"ms_per_launch": ms_hbma, "frames_per_launch": B,
                      "algorithmic_bytes": hbma_bytes, "gbs": hbma_bytes / ms_hbma / 1e6},
         }
-        traffic = None
-        try:  # DRAM bytes of this kernel from the committed ncu --set full capture (same geometry only)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["dct8x8_stream_kernel"]
-            if (W, H) == (1920, 1080) and fused_y:
-                traffic = tj["dram_bytes_per_launch"] * B / tj["frames_per_launch"]
+        # DRAM bytes per launch from the committed `ncu --set full` captures of these kernels
+        # (profiles/traffic.json; same geometry only -- a profiler number, not measured in this run)
+        traffic = {}
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if (W, H, a.levels, a.search_range) == (1920, 1080, 4, 8) and fused_y:
+                for k, v in tj["stages"].items():
+                    traffic[k] = v["dram_bytes_per_launch"] * B / v["frames_per_launch"]
         except Exception:
             pass
-        roofline = {"kernel": "dct8x8_stream_kernel (K3: block DCT + stream records + level-0 luma)",
-                    "bound": "hbm", "achieved": dct_bytes / ms_dct / 1e6, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": dct_bytes / ms_dct / 1e6 / hbm_peak, "traffic": traffic,
-                    "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": dct_bytes}
+        kernels = {"dct_stream_y": "dct8x8_stream_kernel<withY> (K3: block DCT + stream records + level-0 luma)",
+                   "pyr_down": "pyr_down kernels (K1b: pyramid levels 1..L-1 of the batch)",
+                   "hbma": "hbma_tile_kernel<4,1,16> (K2: 4-level search, r = 1; HBM-bound at this range, SURVEY 8d)"}
+        rooflines = {}
+        for k, st_ in stages.items():
+            rooflines[k] = {"kernel": kernels[k], "bound": "hbm", "achieved": st_["gbs"], "peak": hbm_peak,
+                            "unit": "GB/s", "frac": st_["gbs"] / hbm_peak, "traffic": traffic.get(k),
+                            "algorithmic_bytes_per_launch": st_["algorithmic_bytes"]}
+        roofline = dict(rooflines["dct_stream_y"], peak_source=peak_src)
     else:
         roofline = None
+        rooflines = {}
 
     # ---------------- end to end through the host-buffer C-ABI call -------------------
     e2e = None
@@ -400,6 +551,10 @@ def run_ours(a):
                "d2h_bytes_per_step": int(n_enc * (fst + mvn * 12)),
                "ms_per_step": ms_e2e, "steps": n_e2e,
                "api": "svc_session_encode (pinned host buffers; H2D | kernels | D2H pipelined)"}
+        if not a.no_parity:
+            par_out["e2e_host_buffers"] = (h_mv.view(np.float32, (n_enc, sess.mv_field_h, sess.mv_field_w, 2)),
+                                           h_mad.view(np.float32, (n_enc, sess.mv_field_h, sess.mv_field_w)),
+                                           h_st.view(np.uint8, (n_enc, fst)).__getitem__)
     # ---------------- SAD-bound corner of the range sweep (BASELINE config 3), N=1 only ----------
     # The default configuration's search (r = 1) is HBM-bound; the metric also asks for the SAD
     # rate against the integer roofline, so the search kernel is timed alone at R=64, L=1 on
@@ -449,12 +604,13 @@ def run_ours(a):
     work = None
     if rank == 0 and world == 1 and not a.no_cpu:
         from oracle import oracle as O
-        n = max(2, min(a.cpu_sample_frames, F))
+        n = max(2, min(a.cpu_sample_frames or F, F))
         threads = host_cores()
-        fps, dt, what = cpu_hot_path_fps(a, frames[:n], threads)
+        fps, dt, what, split = cpu_hot_path_fps(a, frames[:n], threads)
         cpu = {"value": fps, "unit": UNIT, "cores": threads,
                "kind": "port",
-               "sample": f"first {n} input frames ({n - 1} encoded) of the workload, {dt:.2f} s; {what}"}
+               "sample": f"first {n} input frames ({n - 1} encoded) of the workload, {dt:.2f} s; {what}",
+               "stage_split": split}
         pw, ph = sess.padded_w, sess.padded_h
         nc = na = 0
         k = min(n, 5)
@@ -470,24 +626,40 @@ def run_ours(a):
             work["hbma_gcand_per_s"] = work["candidates_per_frame"] * fps_hbma / 1e9
             work["hbma_gabsdiff_per_s"] = work["absdiffs_per_frame"] * fps_hbma / 1e9
 
+    # ---------------- parity of the measured workload (every rank checks its own shard) ----------------
+    parity = None
+    if par_out:
+        thr = max(1, host_cores() // world)
+        parity = check_parity(a, frames, par_out, sess.padded_w, sess.padded_h, thr)
+        if world > 1:
+            flags = torch.tensor([1.0 if parity["ok"] else 0.0, -parity["dct_max_abs_err"]],
+                                 dtype=torch.float64, device="cuda")
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+            all_ok = bool(flags[0].item() > 0.5)
+            parity["dct_max_abs_err"] = float(-flags[1].item())
+            parity["mv_frames"] = world * n_enc
+            if not all_ok:
+                parity["ok"] = parity["mv_bit_exact"] = parity["mad_bit_exact"] = False
+                parity["note"] = "a rank other than 0 reported a mismatch"
+        if not parity["ok"]:
+            print(f"bench.py: rank {rank}: PARITY MISMATCH {json.dumps(parity)}", file=sys.stderr, flush=True)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "frames_per_step_per_gpu": n_enc,
-                       "batch_frames_per_launch": a.batch,
-                       "l2": "per-step working set (%.1f GB in + %.1f GB out per GPU) far exceeds the "
-                             "126 MB L2; no explicit flush" % (F * fin / 1e9, n_enc * fst / 1e9),
-                       "sharding": "contiguous frame ranges, one overlap frame, no collective",
-                       "host_numa_binding": numa},
+            "config": config_dict(a),
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu, "stages": stages, "sad_work": work, "sad_roofline": sad_roofline,
+            "cpu_baseline": cpu, "parity": parity, "rooflines": rooflines, "stages": stages,
+            "sad_work": work, "sad_roofline": sad_roofline, "host": {"numa_binding": numa, "cores": host_cores()},
         }
         print(json.dumps(line), flush=True)
     sess.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -156,7 +156,17 @@ typedef struct svc_session_config {
   int32_t device;     /* CUDA ordinal */
   uint32_t max_batch; /* frames per launch batch (0 = default 32) */
   void* cuda_stream;  /* cudaStream_t to run on; NULL = session-owned stream */
+  /* Test hook (the only one; nothing in the library reads the environment): restrict the motion-search
+   * dispatcher to one kernel family so that parity tests can reach kernels the dispatcher would not
+   * pick for a configuration.  SVC_HBMA_FAMILY_AUTO (0) = fastest kernel for the configuration.
+   * A caller compiled against the older struct (struct_size without this field) gets AUTO. */
+  uint32_t hbma_kernel_family;
 } svc_session_config;
+
+#define SVC_HBMA_FAMILY_AUTO 0u
+#define SVC_HBMA_FAMILY_GENERIC 1u /* hbma_generic_kernel: any block shape / level count / range */
+#define SVC_HBMA_FAMILY_POOL 2u    /* single-launch pooled kernel (16x16 blocks, r = 5..64) */
+#define SVC_HBMA_FAMILY_WINDOW 3u  /* per-block TMA window kernels (16x16 blocks) */
 
 typedef struct svc_session_info {
   uint32_t padded_w, padded_h;       /* libs/encoder.cpp:166-169 */

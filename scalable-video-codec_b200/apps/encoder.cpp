@@ -141,7 +141,7 @@ int main(int argc, char** argv) {
       svc::Frame f(fbytes);
       for (unsigned i = 0; i < frames; ++i) {
         if (std::fread(f.data(), 1, fbytes, in) != fbytes) break;
-        in_queue.Push(f);
+        if (!in_queue.Push(f)) break;  // closed: the encoder failed
       }
       in_queue.SignalProducerIsDone();
     });
@@ -160,8 +160,8 @@ int main(int argc, char** argv) {
     } catch (const std::exception& e) {
       std::fprintf(stderr, "svc_encoder: %s\n", e.what());
       rc = EXIT_FAILURE;
-      in_queue.SignalProducerIsDone();
-      out_queue.SignalProducerIsDone();
+      in_queue.Close();  // (the encoder closed both already; harmless to repeat)
+      out_queue.Close();
     }
     reader.join();
     writer.join();

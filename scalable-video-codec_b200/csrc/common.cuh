@@ -47,6 +47,8 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
                             uint32_t n_frames, cudaStream_t st);
 
 // ---- K2: hierarchical block matching ---------------------------------------
+// svc_session_config.hbma_kernel_family (include/svc_b200.h: SVC_HBMA_FAMILY_*)
+enum : uint32_t { kHbmaAuto = 0, kHbmaGeneric = 1, kHbmaPool = 2, kHbmaWindow = 3 };
 struct HbmaParams {
   const uint8_t* pyr;  // slot array; frame i: tracked = slot i, anchor = slot i+1
   PyrLayout lay;
@@ -56,10 +58,7 @@ struct HbmaParams {
   float2* mv;   // n_frames x mvh x mvw, may be null
   float* mad;   // n_frames x mvh x mvw, may be null
   uint32_t n_frames;
-  uint32_t force_generic;  // 1 = always take the universal kernel (tests)
-  // > 0: the search co-runs with another kernel (the session's motion stream next to K3): persistent
-  // small-footprint CTAs, this many per SM (default configuration only; 0 = one CTA per tile)
-  uint32_t corun_ctas_per_sm;
+  uint32_t family;  // kHbma*: restrict the dispatcher to one kernel family (test hook; 0 = automatic)
   // optional exact work counters: [0] += candidates, [1] += byte-absdiffs
   unsigned long long* counters;
 };

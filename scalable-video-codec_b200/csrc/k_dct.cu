@@ -877,13 +877,8 @@ cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* nl) {
       const uint64_t units = (uint64_t)((nbx * nby_total + unit - 1) / unit) * p.n_frames;
       if (units > 0x7fffffffull) return cudaErrorInvalidValue;
       YOut yo{p.y_l0, p.y_slot_bytes, p.y_first_slot, p.y_pitch};
-      // occupancy knob (experiment hook): extra dynamic shared memory per CTA leaves room on the
-      // SM for the motion-stream kernels that run concurrently
-      static const char* env_pad = getenv("SVC_DCT_SMEM_PAD");
-      const size_t pad = env_pad ? (size_t)atoi(env_pad) : 0;
       if (tb == 16) {
-        static const char* env_it = getenv("SVC_DCT16_ITER");  // experiment hook: units per CTA
-        const uint32_t upc = env_it && atoi(env_it) > 0 ? (uint32_t)atoi(env_it) : (uint32_t)kIter16;
+        const uint32_t upc = (uint32_t)kIter16;  // units per CTA
         const uint32_t grid = (uint32_t)((units + upc - 1) / upc);
         auto magic64 = [](uint32_t d) { return d > 1u ? ~0ull / d + 1ull : 0ull; };  // ceil(2^64 / d)
         const Div16 dv{magic64((nbx * nby_total + kUnit16 - 1) / kUnit16), magic64(nbx)};
@@ -892,8 +887,8 @@ cudaError_t launch_dct(const DctParams& p, cudaStream_t st, int* nl) {
       } else if (tb == 4) {
         if (with_y) dct4x4_stream_kernel<true><<<(uint32_t)units, kUnit4, 0, st>>>(p, nbx, nby, nby_total, yo);
         else dct4x4_stream_kernel<false><<<(uint32_t)units, kUnit4, 0, st>>>(p, nbx, nby, nby_total, yo);
-      } else if (with_y) dct8x8_stream_kernel<true><<<(uint32_t)units, 96, pad, st>>>(p, nbx, nby, nby_total, yo);
-      else dct8x8_stream_kernel<false><<<(uint32_t)units, 96, pad, st>>>(p, nbx, nby, nby_total, yo);
+      } else if (with_y) dct8x8_stream_kernel<true><<<(uint32_t)units, 96, 0, st>>>(p, nbx, nby, nby_total, yo);
+      else dct8x8_stream_kernel<false><<<(uint32_t)units, 96, 0, st>>>(p, nbx, nby, nby_total, yo);
       if (nl) *nl += 1;
       e = cudaGetLastError();
       if (e != cudaSuccess) return e;

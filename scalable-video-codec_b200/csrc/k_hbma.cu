@@ -17,7 +17,6 @@
 // the argmin runs on integers and only the winner is converted.
 #include <cuda.h>
 #include <float.h>
-#include <stdlib.h>
 
 #include <algorithm>
 
@@ -431,82 +430,6 @@ hbma_tile_kernel(const __grid_constant__ HbmaTileMaps maps, const HbmaParams p) 
 }
 
 // ---------------------------------------------------------------------------
-// Co-running variant of the tiled kernel for the session's motion stream.  Inside a session the
-// search of batch k runs while K3 (HBM-bound, FMA pipe) transforms batch k+1; K3 fills every SM with
-// 9 CTAs x 24.7 KB of shared memory, so the 40 KB tiles above only get onto an SM in K3's tail.  Here
-// a tile is TBY block rows (2: 64 threads, <= 25.6 KB -- exactly the slot one retiring K3 CTA frees)
-// and the grid is a fixed number of persistent CTAs per SM that walk the tiles round robin: the
-// high-priority motion stream places them as K3 CTAs retire, they stay for the whole search
-// (integer-ALU / shared-memory bound, little HBM traffic) and K3 keeps the remaining slots.
-// ---------------------------------------------------------------------------
-template <int L, int R, int BB, int TBYv>
-__global__ void __launch_bounds__(TileGeom<L, R, BB, TBYv>::kThreads)
-hbma_tile_persistent_kernel(const __grid_constant__ HbmaTileMaps maps, const HbmaParams p, const uint32_t n_tx,
-                            const uint32_t n_ty, const uint32_t n_tiles) {
-  using Gm = TileGeom<L, R, BB, TBYv>;
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
-  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int g = min(lane / Gm::G, Gm::BPW - 1);
-  const int dxi = lane - (lane / Gm::G) * Gm::G;
-  const bool owner = (lane / Gm::G) < Gm::BPW && dxi == 0;
-  uint32_t phase = 0;
-  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const uint32_t f = t / (n_tx * n_ty), rem = t - f * (n_tx * n_ty);
-    const int tile_by0 = (int)(rem / n_tx) * Gm::TBY, tile_bx0 = (int)(rem % n_tx) * Gm::TBX;
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
-                   "r"((uint32_t)Gm::tx_bytes()) : "memory");
-#pragma unroll
-      for (int l = 0; l < L; ++l) {
-        const int b = BB >> l;
-        const uint32_t dt = (uint32_t)__cvta_generic_to_shared(smem + Gm::off_t(l));
-        const uint32_t da = (uint32_t)__cvta_generic_to_shared(smem + Gm::off_a(l));
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(dt), "l"(&maps.t[l]), "r"((tile_bx0 * b - Gm::d(l)) & ~15), "r"(tile_by0 * b - Gm::d(l)),
-            "r"((int)f), "r"(bar_addr) : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(da), "l"(&maps.a[l]), "r"((tile_bx0 * b) & ~15), "r"(tile_by0 * b), "r"((int)f + 1),
-            "r"(bar_addr) : "memory");
-      }
-    }
-    {
-      uint32_t done = 0;
-      while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar_addr), "r"(phase) : "memory");
-      }
-    }
-    phase ^= 1u;
-    int mx = 0, my = 0;
-    float cur = FLT_MAX;
-    if constexpr (L >= 5) tile_level<L, R, BB, 4, TBYv>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
-    if constexpr (L >= 4) tile_level<L, R, BB, 3, TBYv>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
-    if constexpr (L >= 3) tile_level<L, R, BB, 2, TBYv>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
-    if constexpr (L >= 2) tile_level<L, R, BB, 1, TBYv>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
-    tile_level<L, R, BB, 0, TBYv>(smem, p, g, dxi, w, tile_bx0, tile_by0, mx, my, cur);
-    const uint32_t bx = (uint32_t)(tile_bx0 + g), by = (uint32_t)(tile_by0 + w);
-    if (owner && bx < p.mvw && by < p.mvh) {
-      const uint64_t o = ((uint64_t)f * p.mvh + by) * p.mvw + bx;
-      if (p.mv) p.mv[o] = make_float2((float)mx, (float)my);
-      if (p.mad) p.mad[o] = cur;
-    }
-    __syncthreads();  // every warp is done with the windows before the next tile's TMA lands
-  }
-}
-
-// ---------------------------------------------------------------------------
 // Window kernel (16x16 blocks, large top-level range r: the range / level sweep
 // of BASELINE config 3).  One CTA per motion block walks the pyramid.  At each
 // level the clamped search window ((B+2r)^2 bytes, position data dependent on
@@ -853,32 +776,6 @@ cudaError_t launch_tile_upper3(const HbmaParams& p, cudaStream_t st) {
   return cudaErrorInvalidValue;
 }
 
-// persistent co-running variant (see hbma_tile_persistent_kernel): ctas_per_sm persistent CTAs per SM
-template <int L, int R, int BB, int TBYv>
-static cudaError_t launch_tile_persistent(const HbmaParams& p, cudaStream_t st, int ctas_per_sm) {
-  using Gm = TileGeom<L, R, BB, TBYv>;
-  static_assert(Gm::ok(), "tile geometry does not fit");
-  HbmaTileMaps maps;
-  const uint32_t n_slots = p.n_frames + 1;
-  for (int l = 0; l < L; ++l) {
-    const uint8_t* base = p.pyr + p.lay.off[l];
-    if (!encode_box(&maps.t[l], base, p.lay.w[l], p.lay.h[l], p.lay.pitch[l], p.lay.slot_bytes,
-                    n_slots, Gm::tw(l), Gm::th(l)) ||
-        !encode_box(&maps.a[l], base, p.lay.w[l], p.lay.h[l], p.lay.pitch[l], p.lay.slot_bytes,
-                    n_slots, Gm::aw(l), Gm::ah(l)))
-      return cudaErrorNotSupported;
-  }
-  auto kern = hbma_tile_persistent_kernel<L, R, BB, TBYv>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::smem_bytes());
-  if (e != cudaSuccess) return e;
-  const uint32_t n_tx = (p.mvw + Gm::TBX - 1) / Gm::TBX, n_ty = (p.mvh + Gm::TBY - 1) / Gm::TBY;
-  const uint64_t n_tiles = (uint64_t)n_tx * n_ty * p.n_frames;
-  if (n_tiles > 0x7fffffffull) return cudaErrorInvalidValue;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)kNumSms * ctas_per_sm);
-  kern<<<grid, Gm::kThreads, Gm::smem_bytes(), st>>>(maps, p, n_tx, n_ty, (uint32_t)n_tiles);
-  return cudaGetLastError();
-}
-
 // (levels, r) pairs with a tiled instantiation; everything else takes the generic kernel
 static bool try_launch_tile(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
   if (p.n_frames > 65535 || (p.mvh + 3) / 4 > 65535) return false;
@@ -893,10 +790,6 @@ static bool try_launch_tile(const HbmaParams& p, cudaStream_t st, cudaError_t* e
     return false;
   }
   if (p.bw != 16 || p.bh != 16) return false;
-  if (L == 4 && r == 1 && p.corun_ctas_per_sm > 0) {  // session motion stream, default configuration
-    *err = launch_tile_persistent<4, 1, 16, 2>(p, st, (int)p.corun_ctas_per_sm);
-    return true;
-  }
 #define SVC_TILE_CASE(LL, RR) \
   if (L == LL && r == RR) { *err = launch_tile<LL, RR>(p, st); return true; }
   SVC_TILE_CASE(4, 1) SVC_TILE_CASE(4, 2) SVC_TILE_CASE(4, 3) SVC_TILE_CASE(4, 4)
@@ -936,8 +829,7 @@ static bool try_launch_window(const HbmaParams& p, cudaStream_t st, cudaError_t*
   g.off_sads = g.off_anchor + 256;
   g.smem_bytes = g.off_sads + (((2 * r + 1) * (2 * r + 1) * 2 + 127) & ~127u);
   if (g.smem_bytes > 200 * 1024) return false;
-  static const bool no_warp = getenv("SVC_HBMA_NO_WARP_WINDOW") != nullptr;  // experiment hook
-  if (g.smem_bytes <= 7 * 1024 && !no_warp) {
+  if (g.smem_bytes <= 7 * 1024) {
     // small windows: one warp per motion block, 8 blocks per CTA
     const uint32_t ctas = (uint32_t)((n_ctas + kWinWarps - 1) / kWinWarps);
     // rows of candidates per work item: the divisor-like choice that wastes the fewest SAD
@@ -976,10 +868,14 @@ static bool try_launch_window(const HbmaParams& p, cudaStream_t st, cudaError_t*
 
 cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches) {
   if (p.n_frames == 0) return cudaSuccess;
-  static const bool env_generic = getenv("SVC_HBMA_FORCE_GENERIC") != nullptr;  // test hook
-  if (!p.force_generic && !env_generic) {
+  // p.family (svc_session_config.hbma_kernel_family, a test hook): 0 = pick the fastest kernel for
+  // the configuration; otherwise only the named family is tried, then the universal kernel.
+  if (p.family != kHbmaGeneric) {
     cudaError_t e = cudaSuccess;
-    if (try_launch_tile(p, st, &e) || try_launch_pool(p, st, &e, n_launches) || try_launch_window(p, st, &e)) {
+    const bool any = p.family == kHbmaAuto;
+    if ((any && try_launch_tile(p, st, &e)) ||
+        ((any || p.family == kHbmaPool) && try_launch_pool(p, st, &e, n_launches)) ||
+        ((any || p.family == kHbmaWindow) && try_launch_window(p, st, &e))) {
       if (n_launches) *n_launches += 1;
       return e;
     }

@@ -28,7 +28,6 @@
 //     (libs/motion.cpp:333-337) is checked with warp shuffles between neighbouring columns;
 //     only items on a warp or window-row boundary go through (small) shared-memory arrays.
 #include <float.h>
-#include <stdlib.h>
 
 #include <algorithm>
 
@@ -1069,12 +1068,12 @@ static cudaError_t launch_pool(const HbmaParams& p, cudaStream_t st) {
 }
 
 bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int* extra_launches) {
-  static const bool off = getenv("SVC_HBMA_NO_POOL") != nullptr;  // experiment hook
   const uint32_t L = p.lay.levels, r = p.r;
-  // r <= 4: hbma_tile_kernel, or (5 levels, r = 3, 4: the reach does not fit a tile) the warp-per-block
-  // window kernel of k_hbma.cu, which measures faster than per-level launches on such small windows
-  static const bool no_hybrid = getenv("SVC_HBMA_NO_HYBRID") != nullptr;  // experiment hook
-  if (!off && !no_hybrid && p.bw == 16 && p.bh == 16 && L == 5 && (r == 3 || r == 4) && p.mv && p.mad &&
+  // p.family == kHbmaPool (test hook): the single-launch pooled kernel wherever it is defined, so that
+  // its parity tests also cover configurations the dispatcher gives to faster kernels
+  const bool force = p.family == kHbmaPool;
+  // r <= 4: hbma_tile_kernel, or (5 levels, r = 3, 4: the reach does not fit a tile) the hybrid below
+  if (!force && p.bw == 16 && p.bh == 16 && L == 5 && (r == 3 || r == 4) && p.mv && p.mad &&
       p.n_frames <= 65535 && (uint64_t)p.mvw * p.mvh * p.n_frames <= 0x7fffffffull) {
     // tile kernel over levels 4..2, then one refinement launch per remaining level
     *err = launch_tile_upper3(p, st);
@@ -1083,71 +1082,40 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int
     if (extra_launches) *extra_launches += 2;
     return true;
   }
-  if (off || p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > (L == 1 ? 112u : 64u)) return false;
+  if (p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > (L == 1 ? 112u : 64u)) return false;
   if ((uint64_t)p.mvw * p.mvh * p.n_frames > 0x7fffffffull) return false;
-  static const bool no_levels = getenv("SVC_HBMA_NO_LEVELS") != nullptr;  // experiment hook
-  if (L >= 2 && r <= 32 && p.mv && p.mad && !no_levels && getenv("SVC_HBMA_FORCE_POOL") == nullptr) {
+  if (L >= 2 && r <= 32 && p.mv && p.mad && !force) {
     // one launch per level; <range class, candidate rows per item, blocks per CTA and CTAs per SM of
     // the 16x16 refinement level>
-    static const char* env_lv = getenv("SVC_HBMA_POOL_VARIANT");  // tuning hook
-    const int lv = env_lv ? atoi(env_lv) : 0;
-    if (r <= 8) {
-      if (lv == 1) *err = launch_levels<8, 9, 7, 128, 4>(p, st, extra_launches);
-      else *err = launch_levels<8, 17, 7, 128, 3>(p, st, extra_launches);
-    } else if (r <= 16) {
-      if (lv == 1) *err = launch_levels<16, 11, 3, 160, 4>(p, st, extra_launches);
-      else *err = launch_levels<16, 11, 3, 128, 4>(p, st, extra_launches);
-    } else {
-      if (lv == 1) *err = launch_levels<32, 13, 1, 128, 4>(p, st, extra_launches);
-      else *err = launch_levels<32, 13, 2, 128, 3>(p, st, extra_launches);
-    }
+    if (r <= 8) *err = launch_levels<8, 17, 7, 128, 3>(p, st, extra_launches);
+    else if (r <= 16) *err = launch_levels<16, 11, 3, 128, 4>(p, st, extra_launches);
+    else *err = launch_levels<32, 13, 2, 128, 3>(p, st, extra_launches);
     return true;
   }
-  // Deep pyramids with a small top-level range are dominated by the per-level fixed costs (TMA
-  // round trip, copy build, barriers) of the small coarse levels: the warp-per-block window
-  // kernel of k_hbma.cu, which has no block-wide barrier, measures a little faster there.
-  const bool force = getenv("SVC_HBMA_FORCE_POOL") != nullptr;  // test / experiment hook (read per launch)
-  if (L >= 3 && r <= 16 && !force) return false;
-  static const char* env_v = getenv("SVC_HBMA_POOL_VARIANT");  // tuning hook
-  const int variant = env_v ? atoi(env_v) : 0;
-  // <range class, blocks per CTA, candidate rows per item, threads, CTAs per SM>: measured best of
-  // several shapes per class on B200 (profiles/r01_sweep_hbma_v12.md)
-  static const bool no_tile = getenv("SVC_HBMA_NO_EBMA_TILE") != nullptr;  // experiment hook
-  if (L == 1 && r > 32 && !no_tile) {
+  // <range class, ..., candidate rows per item, threads, CTAs per SM>: measured best of several shapes
+  // per class on B200 (profiles/r01_sweep_hbma_v12.md)
+  if (L == 1 && r > 32 && !force) {
     // <range class, stripe width in candidate columns, candidate rows per item, threads, CTAs per SM>
-    if (variant == 1) *err = launch_ebma_stripe<64, 43, 13, 128, 4>(p, st);
-    else if (variant == 4) return false;  // the per-block kernels below / in k_hbma.cu
-    else if (r > 64) *err = launch_ebma_stripe<112, 65, 13, 128, 2>(p, st);
+    if (r > 64) *err = launch_ebma_stripe<112, 65, 13, 128, 2>(p, st);
     else *err = launch_ebma_stripe<64, 65, 13, 128, 3>(p, st);
     return true;
   }
-  if (L == 1 && r <= 32 && !no_tile) {
+  if (L == 1 && r <= 32 && !force) {
     // <range class, blocks per tile, candidate rows per item, threads, CTAs per SM>
-    if (r <= 8) {
-      if (variant == 1) *err = launch_ebma_tile<8, 5, 17, 96, 4>(p, st);
-      else *err = launch_ebma_tile<8, 5, 9, 96, 6>(p, st);
-    } else if (r <= 16) {
-      if (variant == 1) *err = launch_ebma_tile<16, 5, 11, 256, 2>(p, st);
-      else *err = launch_ebma_tile<16, 5, 11, 128, 4>(p, st);
-    } else {
-      if (variant == 1) *err = launch_ebma_tile<32, 4, 13, 224, 2>(p, st);
-      else *err = launch_ebma_tile<32, 3, 13, 128, 4>(p, st);
-    }
+    if (r <= 8) *err = launch_ebma_tile<8, 5, 9, 96, 6>(p, st);
+    else if (r <= 16) *err = launch_ebma_tile<16, 5, 11, 128, 4>(p, st);
+    else *err = launch_ebma_tile<32, 3, 13, 128, 4>(p, st);
     return true;
   }
-  if (r <= 8) {
-    if (variant == 1) *err = launch_pool<8, 8, 9, 128, 3>(p, st);
-    else *err = launch_pool<8, 7, 17, 128, 3>(p, st);
-  } else if (r <= 16) {
-    if (variant == 1) *err = launch_pool<16, 4, 11, 128, 3>(p, st);
-    else *err = launch_pool<16, 3, 11, 128, 4>(p, st);
-  } else if (r <= 32) {
-    if (variant == 1) *err = launch_pool<32, 3, 13, 256, 2>(p, st);
-    else *err = launch_pool<32, 2, 13, 128, 3>(p, st);
-  } else {
-    if (variant == 1) *err = launch_pool<64, 1, 10, 256, 2>(p, st);
-    else *err = launch_pool<64, 1, 13, 256, 2>(p, st);
-  }
+  if (r > 64) return false;  // L = 1, r = 65..112 exists only as the striped kernel
+  // Deep pyramids with a small top-level range and only one output wanted (no level-synchronous path):
+  // the warp-per-block window kernel of k_hbma.cu, which has no block-wide barrier, measures faster.
+  if (L >= 3 && r <= 16 && !force) return false;
+  // <range class, blocks per CTA, candidate rows per item, threads, CTAs per SM>
+  if (r <= 8) *err = launch_pool<8, 7, 17, 128, 3>(p, st);
+  else if (r <= 16) *err = launch_pool<16, 3, 11, 128, 4>(p, st);
+  else if (r <= 32) *err = launch_pool<32, 2, 13, 128, 3>(p, st);
+  else *err = launch_pool<64, 1, 13, 256, 2>(p, st);
   return true;
 }
 

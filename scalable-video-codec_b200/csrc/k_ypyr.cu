@@ -11,7 +11,6 @@
 //                                                      BORDER_REFLECT_101
 // All arithmetic is integer and bit-exact with OpenCV's 8-bit paths.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -315,11 +314,10 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
         dw, dh, lay.pitch[l + 1]);
     return cudaGetLastError();
   }
-  static const char* env_thr = getenv("SVC_PYR_BIG_MPIX");  // tuning hooks
-  static const char* env_rpt = getenv("SVC_PYR_BIG_RPT");
-  const uint64_t thr = env_thr ? (uint64_t)atoll(env_thr) << 20 : (8ull << 20);
-  const bool big = (uint64_t)dw * dh * n_frames >= thr;
-  const int rpt = big ? (env_rpt ? atoi(env_rpt) : 8) : 2;
+  // 8 destination rows per thread once the launch holds >= 8 Mi output pixels (throughput-bound),
+  // 2 for small launches (bound by the latency of one CTA)
+  const bool big = (uint64_t)dw * dh * n_frames >= (8ull << 20);
+  const int rpt = big ? 8 : 2;
   const uint32_t tile_h = 4u * (uint32_t)rpt;
   // source level as a 3-D tensor (x, y, slot); box = the tile's source region
   static PyrEncodeTiledFn encode = nullptr;
@@ -345,7 +343,6 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
   pyr_down_kernel<RPT><<<grid, block, 0, st>>>(map, d_pyr, lay.slot_bytes, first_slot, lay.w[l],   \
                                                lay.h[l], lay.off[l + 1], dw, dh, lay.pitch[l + 1])
   if (rpt == 8) SVC_PYR_LAUNCH(8);
-  else if (rpt == 4) SVC_PYR_LAUNCH(4);
   else SVC_PYR_LAUNCH(2);
 #undef SVC_PYR_LAUNCH
   return cudaGetLastError();

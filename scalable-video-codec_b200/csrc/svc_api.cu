@@ -7,7 +7,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <stddef.h>
+
 #include <algorithm>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -41,6 +44,8 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
+// once-per-device kernel attributes; sessions on several host threads may get here concurrently
+std::mutex g_prepare_mutex;
 bool g_prepared[64] = {};
 
 int prepare_device(int dev) {
@@ -49,10 +54,32 @@ int prepare_device(int dev) {
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
   if (dev < 0 || dev >= n) return fail(SVC_ERR_CUDA, "no such CUDA device: " + std::to_string(dev));
   CU(cudaSetDevice(dev));
-  if (dev < 64 && !g_prepared[dev]) {
+  std::lock_guard<std::mutex> lock(g_prepare_mutex);
+  if (dev >= 64 || !g_prepared[dev]) {
     CU(prepare_dct_kernels());
-    g_prepared[dev] = true;
+    if (dev < 64) g_prepared[dev] = true;
   }
+  return SVC_OK;
+}
+
+// The stateless entry points run on a per-thread, per-device non-blocking stream: two host threads
+// calling them do not serialise on the legacy default stream (nor synchronise with it).
+struct ThreadStreams {
+  cudaStream_t st[64] = {};
+  ~ThreadStreams() {
+    for (int d = 0; d < 64; ++d)
+      if (st[d] && cudaSetDevice(d) == cudaSuccess) cudaStreamDestroy(st[d]);
+  }
+};
+thread_local ThreadStreams g_streams;
+
+int thread_stream(int dev, cudaStream_t* out) {
+  if (dev < 0 || dev >= 64) {
+    *out = cudaStreamPerThread;
+    return SVC_OK;
+  }
+  if (!g_streams.st[dev]) CU(cudaStreamCreateWithFlags(&g_streams.st[dev], cudaStreamNonBlocking));
+  *out = g_streams.st[dev];
   return SVC_OK;
 }
 
@@ -224,7 +251,9 @@ static int hbma_host(const uint8_t* const* tracked, const uint8_t* const* anchor
   CU(pyr.alloc(2 * lay.slot_bytes + kSlack));
   CU(dmv.alloc(sizeof(float2) * mvw * mvh));
   CU(dmad.alloc(sizeof(float) * mvw * mvh));
-  cudaStream_t st = 0;
+  cudaStream_t st = nullptr;
+  rc = thread_stream(g_device, &st);
+  if (rc) return rc;
   for (uint32_t l = 0; l < levels; ++l) {
     CU(cudaMemcpy2DAsync(pyr.as<uint8_t>() + lay.off[l], lay.pitch[l], tracked[l], lay.w[l],
                          lay.w[l], lay.h[l], cudaMemcpyHostToDevice, st));
@@ -298,7 +327,9 @@ int svc_y_pyramid(const uint8_t* bgr, uint32_t frame_w, uint32_t frame_h, uint32
   const size_t in_bytes = (size_t)frame_w * frame_h * 3;
   CU(in.alloc(in_bytes));
   CU(pyr.alloc(lay.slot_bytes + kSlack));
-  cudaStream_t st = 0;
+  cudaStream_t st = nullptr;
+  rc = thread_stream(g_device, &st);
+  if (rc) return rc;
   CU(cudaMemcpyAsync(in.p, bgr, in_bytes, cudaMemcpyHostToDevice, st));
   CU(launch_bgr_to_y(in.as<uint8_t>(), frame_w, frame_h, pyr.as<uint8_t>(), lay, 0, 1, st));
   for (uint32_t l = 0; l + 1 < level_count; ++l) CU(launch_pyr_down(pyr.as<uint8_t>(), lay, l, 0, 1, st));
@@ -333,7 +364,9 @@ int svc_dct_planar(const uint8_t* bgr, uint32_t frame_w, uint32_t frame_h, uint3
   CU(in.alloc(in_bytes));
   CU(out.alloc(plane_elems * 3 * sizeof(float)));
   CU(tmp.alloc(plane_elems * 3 * sizeof(float)));
-  cudaStream_t st = 0;
+  cudaStream_t st = nullptr;
+  rc = thread_stream(g_device, &st);
+  if (rc) return rc;
   CU(cudaMemcpyAsync(in.p, bgr, in_bytes, cudaMemcpyHostToDevice, st));
   DctParams p{};
   p.bgr = in.as<uint8_t>();
@@ -370,7 +403,9 @@ int svc_encode_frame_stream(const uint8_t* bgr, uint32_t frame_w, uint32_t frame
   CU(in.alloc(in_bytes));
   CU(stream.alloc(sbytes));
   CU(scratch.alloc(plane_elems * 6 * sizeof(float)));
-  cudaStream_t st = 0;
+  cudaStream_t st = nullptr;
+  rc = thread_stream(g_device, &st);
+  if (rc) return rc;
   CU(cudaMemcpyAsync(in.p, bgr, in_bytes, cudaMemcpyHostToDevice, st));
   if (block_types) {
     CU(bt.alloc(sizeof(uint32_t) * mvw * mvh));
@@ -484,7 +519,9 @@ int svc_decode_frame_blocks(const uint8_t* frame_records, uint32_t padded_w, uin
   DevBuf in, out;
   CU(in.alloc(in_bytes));
   CU(out.alloc(out_bytes));
-  cudaStream_t st = 0;
+  cudaStream_t st = nullptr;
+  rc = thread_stream(g_device, &st);
+  if (rc) return rc;
   CU(cudaMemcpyAsync(in.p, frame_records, in_bytes, cudaMemcpyHostToDevice, st));
   rc = svc_decode_frames_device(g_device, st, in.as<uint8_t>(), 1, padded_w, padded_h, tbw, tbh,
                                 fg_quant_step, bg_quant_step, gaze, out.as<float>());
@@ -572,9 +609,16 @@ struct svc_session {
 
 namespace {
 
-bool needs_scratch(const svc_session* s) {
-  return !(s->cfg.transform_block_w == 8 && s->cfg.transform_block_h == 8 &&
-           s->cfg.frame_w == s->info.padded_w);
+// Scratch planes of the generic transform / serializer path, allocated on first use.
+int ensure_scratch(svc_session* s, DctParams& dp) {
+  if (!dct_needs_scratch(dp)) return SVC_OK;
+  if (!s->d_scratch) {
+    s->scratch_frames = std::min<uint32_t>(s->info.max_batch, 16);
+    CU(cudaMalloc(&s->d_scratch, (size_t)s->scratch_frames * 6 * dp.pw * dp.ph * sizeof(float)));
+  }
+  dp.scratch_planes = s->d_scratch;
+  dp.scratch_frames = s->scratch_frames;
+  return SVC_OK;
 }
 
 // One batch (<= max_batch frames), everything on the device.  K3 (+ fused luma) runs on
@@ -582,7 +626,7 @@ bool needs_scratch(const svc_session* s) {
 // (join_motion) before anything that consumes motion vectors.
 int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, float* d_mv,
                         float* d_mad, uint8_t* d_stream, const uint32_t* d_bt,
-                        uint32_t* n_enc_out, bool k3_follows = false) {
+                        uint32_t* n_enc_out) {
   const uint32_t first_slot = s->have_prev ? 1u : 0u;
   const uint32_t n_enc = s->have_prev ? m : m - 1;
   const uint32_t cur = s->batch_idx & 1u;
@@ -603,12 +647,9 @@ int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, flo
     dp.scratch_planes = s->d_scratch;
     dp.scratch_frames = s->scratch_frames;
   }
-  if (n_enc && d_stream && dct_needs_scratch(dp) && !s->d_scratch) {
-    // e.g. a caller-supplied frame pointer that is not 8-byte aligned
-    s->scratch_frames = std::min<uint32_t>(s->info.max_batch, 16);
-    CU(cudaMalloc(&s->d_scratch, (size_t)s->scratch_frames * 6 * dp.pw * dp.ph * sizeof(float)));
-    dp.scratch_planes = s->d_scratch;
-    dp.scratch_frames = s->scratch_frames;
+  if (n_enc && d_stream) {  // generic transform blocks, padded widths, unaligned frame pointers
+    int rcs = ensure_scratch(s, dp);
+    if (rcs) return rcs;
   }
   const bool fuse_y = n_enc && d_stream && dct_can_fuse_y(dp);
 
@@ -662,10 +703,7 @@ int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, flo
     p.mv = reinterpret_cast<float2*>(d_mv);
     p.mad = d_mad;
     p.n_frames = n_enc;
-    // Experiment hook (read per launch; measured and rejected): persistent
-    // small-footprint search CTAs, this many per SM, co-resident with the next batch's K3.
-    const char* env_corun = getenv("SVC_HBMA_CORUN");
-    if (env_corun && k3_follows) p.corun_ctas_per_sm = (uint32_t)std::max(0, atoi(env_corun));
+    p.family = s->cfg.hbma_kernel_family;
     CU(launch_hbma(p, s->s_aux, &nl));
   }
   CU(cudaEventRecord(s->ev_motion[cur], s->s_aux));
@@ -694,9 +732,29 @@ int fork_motion(svc_session* s) {
   return SVC_OK;
 }
 
-int ensure_staging(svc_session* s) {
-  if (s->staging) return SVC_OK;
-  const size_t B = s->info.max_batch;
+void free_staging(svc_session* s) {
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(s->d_in[b]);
+    cudaFree(s->d_mv[b]);
+    cudaFree(s->d_mad[b]);
+    cudaFree(s->d_st[b]);
+    cudaFree(s->d_bt[b]);
+    s->d_in[b] = s->d_st[b] = nullptr;
+    s->d_mv[b] = s->d_mad[b] = nullptr;
+    s->d_bt[b] = nullptr;
+    if (s->ev_in[b]) cudaEventDestroy(s->ev_in[b]);
+    if (s->ev_comp[b]) cudaEventDestroy(s->ev_comp[b]);
+    if (s->ev_out[b]) cudaEventDestroy(s->ev_out[b]);
+    s->ev_in[b] = s->ev_comp[b] = s->ev_out[b] = nullptr;
+  }
+  if (s->s_in) cudaStreamDestroy(s->s_in);
+  if (s->s_out) cudaStreamDestroy(s->s_out);
+  s->s_in = s->s_out = nullptr;
+  s->staging = false;
+}
+
+int alloc_staging(svc_session* s) {
+  const size_t B = std::min(s->info.max_batch, s->host_chunk);  // svc_session_encode moves host_chunk frames per stage
   const size_t mvn = (size_t)s->info.mv_field_w * s->info.mv_field_h;
   CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
@@ -710,6 +768,21 @@ int ensure_staging(svc_session* s) {
     CU(cudaEventCreateWithFlags(&s->ev_comp[b], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s->ev_out[b], cudaEventDisableTiming));
   }
+  return SVC_OK;
+}
+
+// Host-path staging, created on the first svc_session_encode; a failure half-way releases what
+// was created, so a retry neither leaks nor reuses a partial set.
+int ensure_staging(svc_session* s) {
+  if (s->staging) return SVC_OK;
+  const int rc = alloc_staging(s);
+  if (rc != SVC_OK) {
+    const std::string keep = g_err;
+    free_staging(s);
+    cudaGetLastError();
+    g_err = keep;
+    return rc;
+  }
   s->staging = true;
   return SVC_OK;
 }
@@ -718,10 +791,18 @@ int ensure_staging(svc_session* s) {
 
 extern "C" {
 
-int svc_session_create(const svc_session_config* cfg, svc_session** out) {
-  if (!cfg || !out) return fail(SVC_ERR_INVALID_ARG, "null pointer");
-  if (cfg->struct_size != sizeof(svc_session_config))
+int svc_session_create(const svc_session_config* cfg_in, svc_session** out) {
+  if (!cfg_in || !out) return fail(SVC_ERR_INVALID_ARG, "null pointer");
+  // struct_size versions the struct: fields added after `cuda_stream` default to zero for older callers
+  if (cfg_in->struct_size < offsetof(svc_session_config, hbma_kernel_family) ||
+      cfg_in->struct_size > sizeof(svc_session_config))
     return fail(SVC_ERR_INVALID_ARG, "svc_session_config.struct_size mismatch");
+  svc_session_config cfg_copy{};
+  memcpy(&cfg_copy, cfg_in, cfg_in->struct_size);
+  cfg_copy.struct_size = sizeof(svc_session_config);
+  const svc_session_config* cfg = &cfg_copy;
+  if (cfg->hbma_kernel_family > SVC_HBMA_FAMILY_WINDOW)
+    return fail(SVC_ERR_INVALID_ARG, "hbma_kernel_family must be one of SVC_HBMA_FAMILY_*");
   *out = nullptr;
   // Validate(EncoderConfig), libs/encoder.cpp:62-142 (hot-path fields)
   if (cfg->mv_block_w < 1) return fail(SVC_ERR_INVALID_ARG, "invalid mv block width: must be > 0");
@@ -795,7 +876,6 @@ int svc_session_create(const svc_session_config* cfg, svc_session** out) {
     // batch are placed first, so the ALU-bound motion work co-runs with the HBM-bound K3
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (getenv("SVC_MOTION_LOW_PRIORITY")) prio_hi = prio_lo;  // experiment hook
     e = cudaStreamCreateWithPriority(&s->s_aux, cudaStreamNonBlocking, prio_hi);
   }
   if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamCreate(motion)"));
@@ -805,12 +885,8 @@ int svc_session_create(const svc_session_config* cfg, svc_session** out) {
   if (e != cudaSuccess) return bail(cuda_fail(e, "cudaEventCreate"));
   e = cudaStreamSynchronize(s->stream);  // the memsets, before the motion stream may touch the arrays
   if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamSynchronize"));
-  if (needs_scratch(s)) {
-    s->scratch_frames = std::min<uint32_t>(s->info.max_batch, 16);
-    e = cudaMalloc(&s->d_scratch, (size_t)s->scratch_frames * 6 * pw * ph * sizeof(float));
-    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(scratch)"));
-  }
-  if (const char* hc = getenv("SVC_HOST_CHUNK")) s->host_chunk = std::max(1, atoi(hc));  // tuning hook
+  // (the scratch planes of the generic transform path are allocated on first use, see
+  // encode_batch_device / svc_session_run_stage: the fused stream kernels never touch them)
   *out = s;
   return SVC_OK;
 }
@@ -819,16 +895,9 @@ void svc_session_destroy(svc_session* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  for (int b = 0; b < 2; ++b) {
-    cudaFree(s->d_in[b]);
-    cudaFree(s->d_mv[b]);
-    cudaFree(s->d_mad[b]);
-    cudaFree(s->d_st[b]);
-    cudaFree(s->d_bt[b]);
-    if (s->ev_in[b]) cudaEventDestroy(s->ev_in[b]);
-    if (s->ev_comp[b]) cudaEventDestroy(s->ev_comp[b]);
-    if (s->ev_out[b]) cudaEventDestroy(s->ev_out[b]);
-  }
+  if (s->s_in) cudaStreamSynchronize(s->s_in);
+  if (s->s_out) cudaStreamSynchronize(s->s_out);
+  free_staging(s);
   if (s->s_aux) cudaStreamSynchronize(s->s_aux);
   cudaFree(s->d_pyrs[0]);
   cudaFree(s->d_pyrs[1]);
@@ -838,8 +907,6 @@ void svc_session_destroy(svc_session* s) {
     if (s->ev_motion[i]) cudaEventDestroy(s->ev_motion[i]);
   if (s->s_aux) cudaStreamDestroy(s->s_aux);
   cudaFree(s->d_scratch);
-  if (s->s_in) cudaStreamDestroy(s->s_in);
-  if (s->s_out) cudaStreamDestroy(s->s_out);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   cudaGetLastError();
   delete s;
@@ -884,6 +951,7 @@ int svc_session_hbma_work(svc_session* s, uint32_t n_frames, uint64_t* candidate
   p.mvw = s->info.mv_field_w;
   p.mvh = s->info.mv_field_h;
   p.n_frames = n_frames;
+  p.family = s->cfg.hbma_kernel_family;
   p.counters = cnt.as<unsigned long long>();
   int nl = 0;
   CU(launch_hbma(p, s->stream, &nl));
@@ -923,7 +991,7 @@ int svc_session_encode_device(svc_session* s, const uint8_t* d_frames, uint32_t 
         s, d_frames + (size_t)done_in * s->info.frame_in_bytes, m,
         d_mv ? d_mv + done_enc * mvn * 2 : nullptr, d_mad ? d_mad + done_enc * mvn : nullptr,
         d_stream ? d_stream + (size_t)done_enc * s->info.frame_stream_bytes : nullptr,
-        d_bt ? d_bt + done_enc * mvn : nullptr, &ne, d_stream != nullptr && done_in + m < n_frames);
+        d_bt ? d_bt + done_enc * mvn : nullptr, &ne);
     if (rc) return rc;
     done_in += m;
     done_enc += ne;
@@ -1009,6 +1077,7 @@ int svc_session_run_stage(svc_session* s, int stage, const uint8_t* d_frames, ui
   switch (stage) {
     case SVC_STAGE_Y_PYRAMID: {
       if (!d_frames) return fail(SVC_ERR_INVALID_ARG, "null frames");
+      s->have_prev = false;  // slots of array 0 are overwritten: the encode sequence starts over
       CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, s->d_pyr, s->lay, 1, n_frames, s->stream));
       nl += 1;
       for (uint32_t l = 0; l + 1 < s->lay.levels; ++l) {
@@ -1029,6 +1098,7 @@ int svc_session_run_stage(svc_session* s, int stage, const uint8_t* d_frames, ui
       p.mv = reinterpret_cast<float2*>(d_mv);
       p.mad = d_mad;
       p.n_frames = n_frames;
+      p.family = s->cfg.hbma_kernel_family;
       CU(launch_hbma(p, s->stream, &nl));
       break;
     }
@@ -1044,9 +1114,12 @@ int svc_session_run_stage(svc_session* s, int stage, const uint8_t* d_frames, ui
       p.frame_stream_bytes = s->info.frame_stream_bytes;
       p.mv_block_w = s->cfg.mv_block_w; p.mv_block_h = s->cfg.mv_block_h;
       p.mv_field_w = s->info.mv_field_w; p.mv_field_h = s->info.mv_field_h;
-      p.scratch_planes = s->d_scratch;
-      p.scratch_frames = s->scratch_frames;
+      {
+        int rcs = ensure_scratch(s, p);
+        if (rcs) return rcs;
+      }
       if (dct_can_fuse_y(p)) {  // as inside a step: level-0 luma of slots 1..n rides along
+        s->have_prev = false;   // (overwrites slots of array 0)
         p.y_l0 = s->d_pyr + s->lay.off[0];
         p.y_slot_bytes = s->lay.slot_bytes;
         p.y_first_slot = 1;
@@ -1056,6 +1129,7 @@ int svc_session_run_stage(svc_session* s, int stage, const uint8_t* d_frames, ui
       break;
     }
     case SVC_STAGE_PYR_DOWN: {
+      s->have_prev = false;
       for (uint32_t l = 0; l + 1 < s->lay.levels; ++l) {
         CU(launch_pyr_down(s->d_pyr, s->lay, l, 1, n_frames, s->stream));
         nl += 1;

@@ -56,6 +56,9 @@ static void check(int rc) {
   if (rc != SVC_OK) throw Error(rc, svc_last_error());
 }
 
+void Encoder::SessionDeleter::operator()(svc_session* s) const { svc_session_destroy(s); }
+void Encoder::PinnedDeleter::operator()(void* p) const { svc_host_free(p); }
+
 Encoder::Encoder(const EncoderConfig& cfg, const VideoProperties& vidprops,
                  BoundedQueue<Frame>& in_queue, BoundedQueue<Bytes>& out_queue, BlockTypeFn classify)
     : cfg_(cfg), vidprops_(vidprops), in_queue_(in_queue), out_queue_(out_queue),
@@ -72,9 +75,13 @@ Encoder::Encoder(const EncoderConfig& cfg, const VideoProperties& vidprops,
   c.transform_block_h = cfg.transform_block_h;
   c.device = cfg.device;
   c.max_batch = cfg.max_batch;
-  check(svc_session_create(&c, &session_));
+  {
+    svc_session* raw = nullptr;
+    check(svc_session_create(&c, &raw));
+    session_.reset(raw);
+  }
   svc_session_info info{};
-  check(svc_session_info_get(session_, &info));
+  check(svc_session_info_get(session_.get(), &info));
   padded_frame_w_ = info.padded_w;  // libs/encoder.cpp:165-175
   padded_frame_h_ = info.padded_h;
   mv_field_w_ = info.mv_field_w;
@@ -82,14 +89,14 @@ Encoder::Encoder(const EncoderConfig& cfg, const VideoProperties& vidprops,
   frame_stream_bytes_ = info.frame_stream_bytes;
   frame_in_bytes_ = info.frame_in_bytes;
   const size_t B = info.max_batch, mvn = (size_t)mv_field_w_ * mv_field_h_;
-  h_in_ = static_cast<uchar*>(svc_host_alloc(B * frame_in_bytes_));
+  h_in_.reset(static_cast<uchar*>(svc_host_alloc(B * frame_in_bytes_)));
+  if (!h_in_) throw Error(SVC_ERR_CUDA, "pinned allocation failed");
   for (int k = 0; k < 2; ++k) {
-    h_stream_[k] = static_cast<uchar*>(svc_host_alloc(B * frame_stream_bytes_));
-    h_mv_[k] = static_cast<float*>(svc_host_alloc(B * mvn * 2 * sizeof(float)));
-    h_mad_[k] = static_cast<float*>(svc_host_alloc(B * mvn * sizeof(float)));
+    h_stream_[k].reset(static_cast<uchar*>(svc_host_alloc(B * frame_stream_bytes_)));
+    h_mv_[k].reset(static_cast<float*>(svc_host_alloc(B * mvn * 2 * sizeof(float))));
+    h_mad_[k].reset(static_cast<float*>(svc_host_alloc(B * mvn * sizeof(float))));
     if (!h_stream_[k] || !h_mv_[k] || !h_mad_[k]) throw Error(SVC_ERR_CUDA, "pinned allocation failed");
   }
-  if (!h_in_) throw Error(SVC_ERR_CUDA, "pinned allocation failed");
   if (!classify_ && cfg_.segment) {
     SegmentConfig sc = cfg_.seg;
     sc.mv_block_w = cfg_.mv_block_w;
@@ -98,18 +105,34 @@ Encoder::Encoder(const EncoderConfig& cfg, const VideoProperties& vidprops,
   }
 }
 
-Encoder::~Encoder() {
-  svc_host_free(h_in_);
-  for (int k = 0; k < 2; ++k) {
-    svc_host_free(h_stream_[k]);
-    svc_host_free(h_mv_[k]);
-    svc_host_free(h_mad_[k]);
-  }
-  svc_session_destroy(session_);
-}
+Encoder::~Encoder() = default;  // pinned buffers, then the session (members in reverse order)
 
 void Encoder::operator()() {
-  // Header first (libs/encoder.cpp:361-381): frame_count excludes the tracked-only first frame
+  // Whatever happens below, the consumer of the output queue is released: a normal return
+  // signals completion (libs/encoder.cpp:666); an exception closes BOTH queues, so a reader
+  // blocked in Push on a full input queue and a writer blocked in Pop both wake up.
+  struct Finish {
+    BoundedQueue<Frame>& in;
+    BoundedQueue<Bytes>& out;
+    bool ok = false;
+    ~Finish() {
+      if (ok) {
+        out.SignalProducerIsDone();
+      } else {
+        in.Close();
+        out.Close();
+      }
+    }
+  } finish{in_queue_, out_queue_};
+  // The reference pops the first frame before it emits anything and returns without output
+  // when the input is empty (libs/encoder.cpp:344-348).
+  Frame frame;
+  if (!in_queue_.Pop(frame)) {
+    finish.ok = true;
+    return;
+  }
+  bool have_first = true;
+  // Header next (libs/encoder.cpp:361-381): frame_count excludes the tracked-only first frame
   {
     Bytes hdr(32);
     check(svc_write_header(vidprops_.frame_count, vidprops_.frame_w, vidprops_.frame_h, padded_frame_w_,
@@ -121,8 +144,7 @@ void Encoder::operator()() {
   std::vector<uint> block_types(mvn);
   std::vector<uint> batch_types;
   svc_session_info info{};
-  check(svc_session_info_get(session_, &info));
-  Frame frame;
+  check(svc_session_info_get(session_.get(), &info));
   std::thread post;  // at most one alive: batch k's labels / patching / pushes, in frame order
   std::exception_ptr post_error;
   struct Joiner {
@@ -131,19 +153,20 @@ void Encoder::operator()() {
   } joiner{post};
   for (uint k = 0;; ++k) {
     // block for one frame, then take whatever else is already queued (<= max_batch)
-    if (!in_queue_.Pop(frame)) break;
+    if (!have_first && !in_queue_.Pop(frame)) break;
+    have_first = false;
     uint n = 0;
     do {
       if (frame.size() != frame_in_bytes_) throw Error(SVC_ERR_INVALID_ARG, "frame has the wrong size");
-      std::memcpy(h_in_ + (size_t)n * frame_in_bytes_, frame.data(), frame_in_bytes_);
+      std::memcpy(h_in_.get() + (size_t)n * frame_in_bytes_, frame.data(), frame_in_bytes_);
       ++n;
     } while (n < info.max_batch && in_queue_.TryPop(frame));
     const int set = (int)(k & 1);
-    uchar* h_stream = h_stream_[set];
-    float* h_mv = h_mv_[set];
-    float* h_mad = h_mad_[set];
+    uchar* h_stream = h_stream_[set].get();
+    float* h_mv = h_mv_[set].get();
+    float* h_mad = h_mad_[set].get();
     uint n_enc = 0;
-    check(svc_session_encode(session_, h_in_, n, h_mv, h_mad, h_stream, nullptr, &n_enc));
+    check(svc_session_encode(session_.get(), h_in_.get(), n, h_mv, h_mad, h_stream, nullptr, &n_enc));
     // batch k-1 is out of the other set before batch k+1 may overwrite it, and frames leave in order
     if (post.joinable()) post.join();
     if (post_error) std::rethrow_exception(post_error);
@@ -169,7 +192,8 @@ void Encoder::operator()() {
                                         cfg_.transform_block_h, 3, cfg_.mv_block_w, cfg_.mv_block_h,
                                         mv_field_w_, block_types.data()));
           }
-          out_queue_.Push(Bytes(rec, rec + frame_stream_bytes_));
+          if (!out_queue_.Push(Bytes(rec, rec + frame_stream_bytes_)))
+            throw Error(SVC_ERR_INVALID_ARG, "output queue closed by its consumer");
         }
       } catch (...) {
         post_error = std::current_exception();
@@ -178,7 +202,7 @@ void Encoder::operator()() {
   }
   if (post.joinable()) post.join();
   if (post_error) std::rethrow_exception(post_error);
-  out_queue_.SignalProducerIsDone();  // libs/encoder.cpp:666
+  finish.ok = true;  // -> SignalProducerIsDone, libs/encoder.cpp:666
 }
 
 }  // namespace svc

@@ -73,21 +73,27 @@ Status Validate(const EncoderConfig&);
 
 // Bounded blocking queue with the reference's CircularQueue semantics
 // (libs/queue.hpp:13-83): Push blocks when full, Pop returns false once the
-// queue is empty and the producer signalled completion.
+// queue is empty and the producer signalled completion.  Added for error paths
+// (the reference has none): Close() cancels the queue -- it wakes both sides,
+// Push returns false from then on and Pop returns false immediately, so a
+// producer blocked on a full queue and a consumer blocked on an empty one both
+// leave when the stage between them failed.
 template <typename T>
 class BoundedQueue {
  public:
   explicit BoundedQueue(size_t capacity) : cap_(capacity) {}
-  void Push(T v) {
+  bool Push(T v) {
     std::unique_lock<std::mutex> l(m_);
-    not_full_.wait(l, [&] { return q_.size() < cap_; });
+    not_full_.wait(l, [&] { return q_.size() < cap_ || closed_; });
+    if (closed_) return false;
     q_.push_back(std::move(v));
     not_empty_.notify_one();
+    return true;
   }
   bool Pop(T& out) {
     std::unique_lock<std::mutex> l(m_);
-    not_empty_.wait(l, [&] { return !q_.empty() || done_; });
-    if (q_.empty()) return false;
+    not_empty_.wait(l, [&] { return !q_.empty() || done_ || closed_; });
+    if (closed_ || q_.empty()) return false;
     out = std::move(q_.front());
     q_.pop_front();
     not_full_.notify_one();
@@ -107,11 +113,21 @@ class BoundedQueue {
     done_ = true;
     not_empty_.notify_all();
   }
+  void Close() {
+    std::lock_guard<std::mutex> l(m_);
+    closed_ = done_ = true;
+    not_empty_.notify_all();
+    not_full_.notify_all();
+  }
+  bool closed() {
+    std::lock_guard<std::mutex> l(m_);
+    return closed_;
+  }
 
  private:
   size_t cap_;
   std::deque<T> q_;
-  bool done_ = false;
+  bool done_ = false, closed_ = false;
   std::mutex m_;
   std::condition_variable not_full_, not_empty_;
 };
@@ -146,17 +162,21 @@ class Encoder {
   BoundedQueue<Bytes>& out_queue_;
   BlockTypeFn classify_;
   std::unique_ptr<BlockTypeStage> stage_;
-  svc_session* session_ = nullptr;
+  struct SessionDeleter { void operator()(svc_session* s) const; };
+  struct PinnedDeleter { void operator()(void* p) const; };
+  template <class T> using Pinned = std::unique_ptr<T, PinnedDeleter>;
+  // RAII members: a constructor that throws half-way releases what it already acquired
+  std::unique_ptr<svc_session, SessionDeleter> session_;
   uint padded_frame_w_ = 0, padded_frame_h_ = 0, mv_field_w_ = 0, mv_field_h_ = 0;
   uint64_t frame_stream_bytes_ = 0, frame_in_bytes_ = 0;
   uint64_t frames_encoded_ = 0;
   // pinned staging owned by the encoder (svc_host_alloc)
-  uchar* h_in_ = nullptr;
+  Pinned<uchar> h_in_;
   // two sets of output staging: a post thread labels, patches and pushes batch k out of one set
   // while the GPU encodes batch k+1 into the other
-  uchar* h_stream_[2] = {nullptr, nullptr};
-  float* h_mv_[2] = {nullptr, nullptr};
-  float* h_mad_[2] = {nullptr, nullptr};
+  Pinned<uchar> h_stream_[2];
+  Pinned<float> h_mv_[2];
+  Pinned<float> h_mad_[2];
 };
 
 }  // namespace svc

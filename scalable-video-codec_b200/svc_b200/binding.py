@@ -18,6 +18,8 @@ _f32p = C.POINTER(C.c_float)
 _u32p = C.POINTER(C.c_uint32)
 
 STAGE_Y_PYRAMID, STAGE_HBMA, STAGE_DCT_STREAM, STAGE_PYR_DOWN = 1, 2, 3, 4
+# svc_session_config.hbma_kernel_family (test hook): SVC_HBMA_FAMILY_*
+HBMA_FAMILY_AUTO, HBMA_FAMILY_GENERIC, HBMA_FAMILY_POOL, HBMA_FAMILY_WINDOW = 0, 1, 2, 3
 
 
 class SvcError(RuntimeError):
@@ -36,7 +38,8 @@ class _Cfg(C.Structure):
                 ("mv_block_w", C.c_uint32), ("mv_block_h", C.c_uint32),
                 ("mv_search_range", C.c_uint32), ("pyr_lvl_count", C.c_uint32),
                 ("transform_block_w", C.c_uint32), ("transform_block_h", C.c_uint32),
-                ("device", C.c_int32), ("max_batch", C.c_uint32), ("cuda_stream", C.c_void_p)]
+                ("device", C.c_int32), ("max_batch", C.c_uint32), ("cuda_stream", C.c_void_p),
+                ("hbma_kernel_family", C.c_uint32)]
 
 
 class _Info(C.Structure):
@@ -370,6 +373,7 @@ class SessionConfig:
     device: int = 0
     max_batch: int = 0
     cuda_stream: int = 0
+    hbma_kernel_family: int = 0  # test hook: HBMA_FAMILY_*
 
 
 def _addr(x) -> Optional[int]:
@@ -390,7 +394,8 @@ class Session:
         self.cfg = cfg
         c = _Cfg(C.sizeof(_Cfg), cfg.frame_w, cfg.frame_h, cfg.mv_block_w, cfg.mv_block_h,
                  cfg.mv_search_range, cfg.pyr_lvl_count, cfg.transform_block_w,
-                 cfg.transform_block_h, cfg.device, cfg.max_batch, cfg.cuda_stream or None)
+                 cfg.transform_block_h, cfg.device, cfg.max_batch, cfg.cuda_stream or None,
+                 cfg.hbma_kernel_family)
         h = C.c_void_p()
         _check(lib().svc_session_create(C.byref(c), C.byref(h)))
         self._h = h

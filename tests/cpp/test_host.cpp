@@ -2,6 +2,7 @@
 // against the C oracle (oracle/svc_oracle.c; test infrastructure).
 //   test_host            full run, needs a GPU
 //   test_host --no-gpu   host-only checks (validation text, hard failure without a device)
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -88,6 +89,31 @@ int main(int argc, char** argv) {
       }
       CHECK(next == (n ? n : 1));
     }
+  // ---- BoundedQueue: Close() releases a producer blocked on a full queue and a consumer blocked on
+  // an empty one (the error path of the encoder application) ------------------------------------
+  {
+    svc::BoundedQueue<int> q(2);
+    CHECK(q.Push(1) && q.Push(2));
+    bool push_result = true;
+    std::thread producer([&] { push_result = q.Push(3); });  // blocks: the queue is full
+    std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    q.Close();
+    producer.join();
+    CHECK(!push_result);
+    int v = 0;
+    CHECK(!q.Pop(v) && !q.Push(4) && q.closed());
+    svc::BoundedQueue<int> e(2);
+    bool pop_result = true;
+    std::thread consumer([&] { int x; pop_result = e.Pop(x); });  // blocks: the queue is empty
+    std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    e.Close();
+    consumer.join();
+    CHECK(!pop_result);
+    svc::BoundedQueue<int> d(2);  // SignalProducerIsDone keeps the reference semantics: drain, then false
+    CHECK(d.Push(7));
+    d.SignalProducerIsDone();
+    CHECK(d.Pop(v) && v == 7 && !d.Pop(v));
+  }
   int ndev = 0;
   svc_device_count(&ndev);
   if (no_gpu || ndev == 0) {

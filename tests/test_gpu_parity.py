@@ -146,17 +146,38 @@ def test_hbma_window_path_vs_oracle(gpu, oracle, L, R, w, h):
                                  (2, 16), (2, 34), (2, 64), (2, 128), (3, 32), (3, 64), (3, 128),
                                  (4, 64), (4, 128), (5, 128)])
 @pytest.mark.parametrize("w,h", [(416, 240), (48, 176)])
-def test_hbma_pooled_window_path_vs_oracle(gpu, oracle, L, R, w, h, monkeypatch):
+def test_hbma_pooled_window_path_vs_oracle(gpu, oracle, L, R, w, h):
     """16x16 blocks, top-level range 5..64: the pooled kernel with pre-shifted window copies
     (every range class, ranges inside a class, interior blocks with unclamped windows as well as
-    windows clamped on every side, a frame narrower than the window, flat-patch ties)."""
-    monkeypatch.setenv("SVC_HBMA_FORCE_POOL", "1")  # also where the dispatcher prefers the warp kernel
-    pw, ph = gpu.padded_dim(w, 16, L), gpu.padded_dim(h, 16, L)
+    windows clamped on every side, a frame narrower than the window, flat-patch ties).  The session
+    test hook hbma_kernel_family selects it also where the dispatcher prefers another kernel."""
     seq = SyntheticSequence(w, h, 2, seed=L * 13 + R)
-    p0, p1 = oracle.y_pyramid(seq.frame(0), pw, ph, L), oracle.y_pyramid(seq.frame(1), pw, ph, L)
-    mv, mad = gpu.EstimateMotionHierarchical(p0, p1, L, pw, ph, R, 16, 16)
+    frames = np.stack([seq.frame(0), seq.frame(1)])
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, mv_search_range=R, pyr_lvl_count=L,
+                                       hbma_kernel_family=gpu.HBMA_FAMILY_POOL)) as s:
+        mv, mad, _ = s.encode(frames, want_stream=False)
+        pw, ph = s.padded_w, s.padded_h
+    p0, p1 = oracle.y_pyramid(frames[0], pw, ph, L), oracle.y_pyramid(frames[1], pw, ph, L)
     emv, emad = oracle.hbma(p0, p1, R)
-    assert np.array_equal(mv, emv) and np.array_equal(mad, emad)
+    assert np.array_equal(mv[0], emv) and np.array_equal(mad[0], emad)
+
+
+@pytest.mark.parametrize("family", ["GENERIC", "WINDOW"])
+@pytest.mark.parametrize("L,R", [(1, 8), (2, 16), (4, 8), (4, 64), (5, 64)])
+def test_hbma_kernel_family_hook_vs_oracle(gpu, oracle, family, L, R):
+    """svc_session_config.hbma_kernel_family (the library's one test hook): the universal kernel and
+    the per-block window kernels on configurations the dispatcher gives to faster kernels."""
+    w, h = 272, 144
+    seq = SyntheticSequence(w, h, 3, seed=L * 5 + R)
+    frames = seq.frames()
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, mv_search_range=R, pyr_lvl_count=L,
+                                       hbma_kernel_family=getattr(gpu, "HBMA_FAMILY_" + family))) as s:
+        mv, mad, _ = s.encode(frames, want_stream=False)
+        pw, ph = s.padded_w, s.padded_h
+    pyr = [oracle.y_pyramid(f, pw, ph, L) for f in frames]
+    for i in (1, 2):
+        emv, emad = oracle.hbma(pyr[i - 1], pyr[i], R)
+        assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad)
 
 
 @pytest.mark.parametrize("L,R", [(2, 10), (2, 16), (2, 27), (2, 32), (2, 50), (2, 64), (3, 20), (3, 32), (3, 45),
@@ -510,30 +531,3 @@ def test_stage_entry_points(gpu, oracle):
         for i in (1, 2):  # slot i+1 vs slot i  (slot 0 is the zero-initialised previous frame)
             emv, _ = oracle.hbma(pyr[i - 1], pyr[i], 8)
             assert np.array_equal(mv[i], emv)
-
-
-def test_session_corun_search_variant_is_bit_exact(gpu, oracle, monkeypatch):
-    """SVC_HBMA_CORUN (experiment hook, device-resident path): the persistent two-row tile kernel that
-    co-runs with the next batch's K3 must give the same vectors and MADs as the oracle (several
-    batches per call, the last one on the regular kernel)."""
-    monkeypatch.setenv("SVC_HBMA_CORUN", "3")
-    w, h, n = 352, 208, 9
-    frames = SyntheticSequence(w, h, n, seed=123).frames()
-    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, max_batch=3)) as s:
-        mvn = s.mv_field_w * s.mv_field_h
-        d_in = gpu.DeviceBuffer(0, frames.nbytes)
-        d_mv = gpu.DeviceBuffer(0, (n - 1) * mvn * 8)
-        d_mad = gpu.DeviceBuffer(0, (n - 1) * mvn * 4)
-        d_st = gpu.DeviceBuffer(0, (n - 1) * s.frame_stream_bytes)
-        d_in.upload(frames)
-        assert s.encode_device(d_in, n, d_mv, d_mad, d_st) == n - 1
-        s.synchronize()
-        mv = d_mv.download(np.float32, (n - 1, s.mv_field_h, s.mv_field_w, 2))
-        mad = d_mad.download(np.float32, (n - 1, s.mv_field_h, s.mv_field_w))
-        pw, ph = s.padded_w, s.padded_h
-        pyr = [oracle.y_pyramid(f, pw, ph, 4) for f in frames]
-        for i in range(1, n):
-            emv, emad = oracle.hbma(pyr[i - 1], pyr[i], 8)
-            assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad), i
-        for b in (d_in, d_mv, d_mad, d_st):
-            b.free()
