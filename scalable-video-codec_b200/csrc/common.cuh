@@ -46,6 +46,10 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
                             uint32_t src_level, uint32_t first_slot,
                             uint32_t n_frames, cudaStream_t st);
 
+// every level above 0 of n_frames slots (level 0 -> 1, then the smaller levels two per launch)
+cudaError_t launch_pyr_levels(uint8_t* d_pyr, const PyrLayout& lay, uint32_t first_slot,
+                              uint32_t n_frames, cudaStream_t st, int* n_launches);
+
 // ---- K2: hierarchical block matching ---------------------------------------
 // svc_session_config.hbma_kernel_family (include/svc_b200.h: SVC_HBMA_FAMILY_*)
 enum : uint32_t { kHbmaAuto = 0, kHbmaGeneric = 1, kHbmaPool = 2, kHbmaWindow = 3 };

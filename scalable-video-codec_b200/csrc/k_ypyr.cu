@@ -153,6 +153,53 @@ __device__ __forceinline__ int reflect101_near(int p, int len) {
   return min(max(p, 0), len - 1);
 }
 
+// kRpt vertically adjacent groups of 4 output pixels.  `tcol` points 6 bytes left of the first
+// source column of the group's first output (and is 4-byte aligned): with p[j] = tcol[6 + j], output i
+// of a row is sum_k w[k] p[2i+k] horizontally; source rows r = 0 .. 2 kRpt + 2 at tcol + r * kPitch.
+// The horizontal taps are two packed-byte dot products over the two aligned words they straddle (no
+// shifts, no byte extracts); vertical accumulators hold two 16-bit columns per register: a
+// [1 4 6 4 1]^2 sum is at most 255 * 256 = 65280 (+128 rounding) < 2^16, so the halves never carry.
+template <int kRpt, int kPitch, bool kAlign8>  // kAlign8: tcol (and kPitch) are multiples of 8 -> one LDS.64 for p[2..9]
+__device__ __forceinline__ void pyr_down_rows(const uint8_t* __restrict__ tcol, uint32_t (&out)[kRpt]) {
+  constexpr int kRows = 2 * kRpt + 3;
+  uint32_t acc[kRpt][2];
+#pragma unroll
+  for (int y = 0; y < kRpt; ++y) acc[y][0] = acc[y][1] = 0;
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    const uint32_t a1 = *reinterpret_cast<const uint32_t*>(tcol + r * kPitch + 4);  // p[-2..1]
+    uint32_t b0, b1;  // p[2..5], p[6..9]
+    if constexpr (kAlign8) {
+      const uint2 b = *reinterpret_cast<const uint2*>(tcol + r * kPitch + 8);
+      b0 = b.x;
+      b1 = b.y;
+    } else {
+      b0 = *reinterpret_cast<const uint32_t*>(tcol + r * kPitch + 8);
+      b1 = *reinterpret_cast<const uint32_t*>(tcol + r * kPitch + 12);
+    }
+    const uint32_t c = *reinterpret_cast<const uint32_t*>(tcol + r * kPitch + 16);  // p[10..13]
+    const uint32_t h0 = __dp4a(b0, 0x00010406u, __dp4a(a1, 0x04010000u, 0u));  // p[0..4]
+    const uint32_t h1 = __dp4a(b1, 0x00000001u, __dp4a(b0, 0x04060401u, 0u));  // p[2..6]
+    const uint32_t h2 = __dp4a(b1, 0x00010406u, __dp4a(b0, 0x04010000u, 0u));  // p[4..8]
+    const uint32_t h3 = __dp4a(c, 0x00000001u, __dp4a(b1, 0x04060401u, 0u));   // p[6..10]
+    const uint32_t hp0 = h1 * 65536u + h0, hp1 = h3 * 65536u + h2;
+#pragma unroll
+    for (int y = 0; y < kRpt; ++y) {
+      const int k = r - 2 * y;  // vertical tap index for output row y
+      if (k >= 0 && k <= 4) {
+        const uint32_t wv = (k == 0 || k == 4) ? 1u : ((k == 2) ? 6u : 4u);
+        acc[y][0] += wv * hp0;
+        acc[y][1] += wv * hp1;
+      }
+    }
+  }
+#pragma unroll
+  for (int y = 0; y < kRpt; ++y) {
+    const uint32_t t0 = (acc[y][0] + 0x00800080u) >> 8, t1 = (acc[y][1] + 0x00800080u) >> 8;
+    out[y] = __byte_perm(t0, t1, 0x6420);
+  }
+}
+
 constexpr int kPdTileW = 112;                             // destination tile width (28 lanes x 4)
 constexpr int kPdSrcW = 2 * kPdTileW + 32;                 // 256: cols 2*x0-16 .. 2*x0+239 = the TMA box width
 
@@ -171,7 +218,6 @@ pyr_down_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restrict
                 uint64_t dst_off, uint32_t dw, uint32_t dh, uint32_t dpitch) {
   constexpr int kTileH = 4 * kRpt;
   constexpr int kSrcH = 2 * kTileH + 3;
-  constexpr int kRows = 2 * kRpt + 3;  // source rows per thread
   __shared__ __align__(128) uint8_t tile[kSrcH * kPdSrcW];
   __shared__ __align__(8) uint64_t bar;
   uint8_t* slot = pyr + (uint64_t)(first_slot + blockIdx.z) * slot_bytes;
@@ -233,40 +279,156 @@ pyr_down_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restrict
   const int ox = x0t + 4 * tx, oy = y0t + kRpt * ty;
   if (tx >= kPdTileW / 4 || ox >= (int)dw || oy >= (int)dh) return;
   // source columns 2*ox-2 .. 2*ox+8 live at tile columns 8*tx+14 .. 8*tx+24
-  const uint8_t* tcol = tile + (2 * kRpt * ty) * kPdSrcW + 8 * tx + 8;
-  // vertical accumulators, two 16-bit columns per register: a [1 4 6 4 1]^2 sum is at
-  // most 255 * 256 = 65280 (+128 rounding) < 2^16, so the halves never carry over
-  uint32_t acc[kRpt][2];
+  uint32_t px[kRpt];
+  pyr_down_rows<kRpt, kPdSrcW, true>(tile + (2 * kRpt * ty) * kPdSrcW + 8 * tx + 8, px);
+  uint8_t* drow = slot + dst_off + (uint64_t)oy * dpitch + ox;
 #pragma unroll
-  for (int y = 0; y < kRpt; ++y) acc[y][0] = acc[y][1] = 0;
+  for (int y = 0; y < kRpt; ++y)
+    if (oy + y < (int)dh) *reinterpret_cast<uint32_t*>(drow + (uint64_t)y * dpitch) = px[y];
+}
+
+// ---------------------------------------------------------------------------
+// Two pyramid levels per launch: level l -> l+1 -> l+2 (the small upper levels of a batch, where a
+// launch per level is bound by launch gaps and by the latency of one CTA).  A CTA owns a 24 x 8 tile
+// of level l+2.  It needs the 51 x 19 region of level l+1 around it (cols 2x0-2 .. 2x0+48), which in
+// turn needs 105 x 41 pixels of level l (cols 4x0-6 .. 4x0+98): ONE TMA tensor load (box 144 x 41 from
+// the 16-byte aligned column 4x0-16).  Phase 1 computes the level l+1 region into shared memory (halo
+// included: neighbouring CTAs recompute it) and stores its 48 x 16 core to global memory; phase 2
+// computes the level l+2 tile from it.  Each level is computed from the ROUNDED previous level
+// (cv::buildPyramid, libs/encoder.cpp:470), and BORDER_REFLECT_101 is applied at the edge of each
+// level: level l in the TMA tile as in pyr_down_kernel, level l+1 by reflecting the out-of-image part
+// of the region inside shared memory before phase 2.
+// ---------------------------------------------------------------------------
+constexpr int kF2TileW = 24, kF2TileH = 8;                    // level l+2 tile
+constexpr int kF1W = 2 * kF2TileW + 3, kF1H = 2 * kF2TileH + 3;  // 51 x 19: level l+1 region
+constexpr int kF1Groups = (kF1W + 3) / 4;                     // 13 groups of 4 columns
+constexpr int kF1Rpt = 2, kF1Strips = (kF1H + kF1Rpt - 1) / kF1Rpt;  // 10 strips of 2 rows
+constexpr int kF0BoxW = 144, kF0BoxH = 2 * kF1H + 3;          // 144 x 41: TMA box of level l
+constexpr int kF0Rows = 2 * kF1Rpt * kF1Strips + 3;           // 43: rows the phase-1 threads may touch
+constexpr int kF1Pitch = 64;                                   // level l+1 region: column j at byte j + 2
+constexpr int kFusedThreads = 160;
+static_assert(kF1Groups * kF1Strips <= kFusedThreads, "phase 1 does not fit the CTA");
+static_assert(8 * (kF1Groups - 1) + 4 + 20 <= kF0BoxW, "phase 1 reads past the box");
+
+__global__ void __launch_bounds__(kFusedThreads)
+pyr_down2_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restrict__ pyr, uint64_t slot_bytes,
+                 uint32_t first_slot, uint32_t sw, uint32_t sh, uint64_t off1, uint32_t w1, uint32_t h1,
+                 uint32_t pitch1, uint64_t off2, uint32_t w2, uint32_t h2, uint32_t pitch2) {
+  __shared__ __align__(128) uint8_t tile[kF0Rows * kF0BoxW];
+  __shared__ __align__(16) uint8_t t1[(kF1Rpt * kF1Strips + 1) * kF1Pitch];
+  __shared__ __align__(8) uint64_t bar;
+  uint8_t* slot = pyr + (uint64_t)(first_slot + blockIdx.z) * slot_bytes;
+  const int x0 = blockIdx.x * kF2TileW, y0 = blockIdx.y * kF2TileH;  // level l+2 tile origin
+  const int u0 = 2 * x0 - 2, v0 = 2 * y0 - 2;                        // level l+1 coords of region (0, 0)
+  const int sx0 = 4 * x0 - 16, sy0 = 4 * y0 - 6;                     // level l coords of tile[0][0]
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                 "r"((uint32_t)(kF0BoxH * kF0BoxW)) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"((uint32_t)__cvta_generic_to_shared(tile)), "l"(&src_map), "r"(sx0), "r"(sy0),
+        "r"((int)(first_slot + blockIdx.z)), "r"(bar_addr) : "memory");
+  }
+  __syncthreads();
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar_addr), "r"(0u) : "memory");
+    }
+  }
+  // in-image part of the level l+1 region, and of the level l+2 tile
+  const int ulo = max(u0, 0), uhi = min(u0 + kF1W, (int)w1) - 1;
+  const int vlo = max(v0, 0), vhi = min(v0 + kF1H, (int)h1) - 1;
+  // ---- level l: BORDER_REFLECT_101 rebuilt in shared memory (border CTAs only) --------------
+  {
+    const int r_lo = 2 * vlo - 2, r_hi = 2 * vhi + 2;  // level l rows / columns the valid region reads
+    const int c_lo = 2 * ulo - 2, c_hi = 2 * uhi + 2;
+    if (r_lo < 0 || r_hi >= (int)sh) {  // CTA-uniform
+      for (int i = threadIdx.x; i < (r_hi - r_lo + 1) * (kF0BoxW / 16); i += kFusedThreads) {
+        const int rr = i / (kF0BoxW / 16), ch = i - rr * (kF0BoxW / 16);
+        const int sy = r_lo + rr;
+        if (sy < 0 || sy >= (int)sh) {
+          const int from = reflect101_near(sy, (int)sh) - sy0;
+          *reinterpret_cast<uint4*>(tile + (sy - sy0) * kF0BoxW + ch * 16) =
+              *reinterpret_cast<const uint4*>(tile + from * kF0BoxW + ch * 16);
+        }
+      }
+      __syncthreads();
+    }
+    if (c_lo < 0 || c_hi >= (int)sw) {  // CTA-uniform
+      for (int rr = threadIdx.x; rr <= r_hi - r_lo; rr += kFusedThreads) {
+        uint8_t* trow = tile + (r_lo + rr - sy0) * kF0BoxW - sx0;  // trow[k] = level l column k
+        for (int k = c_lo; k < 0; ++k) trow[k] = trow[reflect101_near(k, (int)sw)];
+        for (int k = max((int)sw, c_lo); k <= c_hi; ++k) trow[k] = trow[reflect101_near(k, (int)sw)];
+      }
+      __syncthreads();
+    }
+  }
+  // ---- phase 1: level l+1 region, 4 columns x 2 rows per thread --------------------------------
+  if (threadIdx.x < kF1Groups * kF1Strips) {
+    const int g = threadIdx.x % kF1Groups, sidx = threadIdx.x / kF1Groups;
+    // region column j = 4g + i reads tile columns 2j + 10 .. 2j + 14 = (8g + 4) + 6 + 2i ..
+    uint32_t px[kF1Rpt];
+    pyr_down_rows<kF1Rpt, kF0BoxW, false>(tile + (2 * kF1Rpt * sidx) * kF0BoxW + 8 * g + 4, px);
 #pragma unroll
-  for (int r = 0; r < kRows; ++r) {
-    const uint32_t a1 = *reinterpret_cast<const uint32_t*>(tcol + r * kPdSrcW + 4);  // tile cols 8tx+12..15
-    const uint2 b = *reinterpret_cast<const uint2*>(tcol + r * kPdSrcW + 8);           // tile cols 8tx+16..23
-    const uint32_t c = *reinterpret_cast<const uint32_t*>(tcol + r * kPdSrcW + 16);     // tile cols 8tx+24..27
-    // p[j] = tile col 8tx+14+j; h[i] = p[2i] + 4 p[2i+1] + 6 p[2i+2] + 4 p[2i+3] + p[2i+4] as two
-    // packed-byte dot products over the two aligned words the five taps straddle
-    const uint32_t h0 = __dp4a(b.x, 0x00010406u, __dp4a(a1, 0x04010000u, 0u));   // cols 14..18
-    const uint32_t h1 = __dp4a(b.y, 0x00000001u, __dp4a(b.x, 0x04060401u, 0u));  // cols 16..20
-    const uint32_t h2 = __dp4a(b.y, 0x00010406u, __dp4a(b.x, 0x04010000u, 0u));  // cols 18..22
-    const uint32_t h3 = __dp4a(c, 0x00000001u, __dp4a(b.y, 0x04060401u, 0u));    // cols 20..24
-    const uint32_t hp0 = h1 * 65536u + h0, hp1 = h3 * 65536u + h2;
-#pragma unroll
-    for (int y = 0; y < kRpt; ++y) {
-      const int k = r - 2 * y;  // vertical tap index for output row y
-      if (k >= 0 && k <= 4) {
-        const uint32_t wv = (k == 0 || k == 4) ? 1u : ((k == 2) ? 6u : 4u);
-        acc[y][0] += wv * hp0;
-        acc[y][1] += wv * hp1;
+    for (int y = 0; y < kF1Rpt; ++y) {
+      const int i1 = kF1Rpt * sidx + y;  // region row
+      // shared copy (column j at byte j + 2: the group sits at byte 4g + 2, 2-byte aligned)
+      uint16_t* q = reinterpret_cast<uint16_t*>(t1 + i1 * kF1Pitch + 4 * g + 2);
+      q[0] = (uint16_t)px[y];
+      q[1] = (uint16_t)(px[y] >> 16);
+      // core of the region -> global memory (u = 2x0 .. 2x0+47, v = 2y0 .. 2y0+15)
+      const int v = v0 + i1, u = u0 + 4 * g;
+      if (i1 >= 2 && i1 < 2 + 2 * kF2TileH && v < (int)h1) {
+        uint8_t* drow = slot + off1 + (uint64_t)v * pitch1;
+        if (g >= 1 && u < (int)w1) *reinterpret_cast<uint16_t*>(drow + u) = (uint16_t)px[y];
+        if (g < kF1Groups - 1 && u + 2 < (int)w1) *reinterpret_cast<uint16_t*>(drow + u + 2) = (uint16_t)(px[y] >> 16);
       }
     }
   }
-  uint8_t* drow = slot + dst_off + (uint64_t)oy * dpitch + ox;
-#pragma unroll
-  for (int y = 0; y < kRpt; ++y) {
-    if (oy + y < (int)dh) {
-      const uint32_t t0 = (acc[y][0] + 0x00800080u) >> 8, t1 = (acc[y][1] + 0x00800080u) >> 8;
-      *reinterpret_cast<uint32_t*>(drow + (uint64_t)y * dpitch) = __byte_perm(t0, t1, 0x6420);
+  __syncthreads();
+  // ---- level l+1: BORDER_REFLECT_101 of the region's out-of-image part ---------------------------
+  {
+    const int xe = min(x0 + kF2TileW, (int)w2), ye = min(y0 + kF2TileH, (int)h2);
+    const int rv_lo = 2 * y0 - 2, rv_hi = 2 * (ye - 1) + 2;  // level l+1 rows / columns the tile reads
+    const int cu_lo = 2 * x0 - 2, cu_hi = 2 * (xe - 1) + 2;
+    if (rv_lo < 0 || rv_hi >= (int)h1) {  // CTA-uniform
+      for (int i = threadIdx.x; i < (rv_hi - rv_lo + 1) * (kF1Pitch / 4); i += kFusedThreads) {
+        const int rr = i / (kF1Pitch / 4), ch = i - rr * (kF1Pitch / 4);
+        const int v = rv_lo + rr;
+        if (v < 0 || v >= (int)h1) {
+          const int from = reflect101_near(v, (int)h1) - v0;
+          *reinterpret_cast<uint32_t*>(t1 + (v - v0) * kF1Pitch + ch * 4) =
+              *reinterpret_cast<const uint32_t*>(t1 + from * kF1Pitch + ch * 4);
+        }
+      }
+      __syncthreads();
+    }
+    if (cu_lo < 0 || cu_hi >= (int)w1) {  // CTA-uniform
+      for (int rr = threadIdx.x; rr <= rv_hi - rv_lo; rr += kFusedThreads) {
+        uint8_t* trow = t1 + (rv_lo + rr - v0) * kF1Pitch + 2 - u0;  // trow[k] = level l+1 column k
+        for (int k = cu_lo; k < 0; ++k) trow[k] = trow[reflect101_near(k, (int)w1)];
+        for (int k = max((int)w1, cu_lo); k <= cu_hi; ++k) trow[k] = trow[reflect101_near(k, (int)w1)];
+      }
+      __syncthreads();
+    }
+  }
+  // ---- phase 2: level l+2 tile, 4 columns x 1 row per thread ------------------------------------
+  if (threadIdx.x < (kF2TileW / 4) * kF2TileH) {
+    const int g = threadIdx.x % (kF2TileW / 4), row = threadIdx.x / (kF2TileW / 4);
+    const int ox = x0 + 4 * g, oy = y0 + row;
+    if (ox < (int)w2 && oy < (int)h2) {
+      // output q = 4g + i reads region columns 2q .. 2q + 4 = bytes 2q + 2 .. = (8g - 4) + 6 + 2i ..
+      uint32_t px[1];
+      pyr_down_rows<1, kF1Pitch, false>(t1 + (2 * row) * kF1Pitch + 8 * g - 4, px);
+      *reinterpret_cast<uint32_t*>(slot + off2 + (uint64_t)oy * pitch2 + ox) = px[0];
     }
   }
 }
@@ -301,6 +463,29 @@ typedef CUresult (*PyrEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                      CUtensorMapFloatOOBfill);
 
+// level `l` of the slot array as a 3-D tensor (x, y, slot) with a box_w x box_h x 1 box
+static cudaError_t encode_level_map(CUtensorMap* map, uint8_t* d_pyr, const PyrLayout& lay, uint32_t l,
+                                    uint32_t n_slots, uint32_t box_w, uint32_t box_h) {
+  static PyrEncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return cudaErrorNotSupported;
+    encode = reinterpret_cast<PyrEncodeTiledFn>(fp);
+  }
+  const cuuint64_t dims[3] = {lay.w[l], lay.h[l], (cuuint64_t)n_slots};
+  const cuuint64_t strides[2] = {lay.pitch[l], lay.slot_bytes};
+  const cuuint32_t box[3] = {box_w, box_h, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  if (encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + lay.off[l], dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorNotSupported;
+  return cudaSuccess;
+}
+
 cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
                             uint32_t src_level, uint32_t first_slot,
                             uint32_t n_frames, cudaStream_t st) {
@@ -319,25 +504,9 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
   const bool big = (uint64_t)dw * dh * n_frames >= (8ull << 20);
   const int rpt = big ? 8 : 2;
   const uint32_t tile_h = 4u * (uint32_t)rpt;
-  // source level as a 3-D tensor (x, y, slot); box = the tile's source region
-  static PyrEncodeTiledFn encode = nullptr;
-  if (!encode) {
-    void* fp = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return cudaErrorNotSupported;
-    encode = reinterpret_cast<PyrEncodeTiledFn>(fp);
-  }
-  CUtensorMap map;
-  const cuuint64_t dims[3] = {lay.w[l], lay.h[l], (cuuint64_t)first_slot + n_frames};
-  const cuuint64_t strides[2] = {lay.pitch[l], lay.slot_bytes};
-  const cuuint32_t box[3] = {(cuuint32_t)kPdSrcW, 2 * tile_h + 3, 1};
-  const cuuint32_t es[3] = {1, 1, 1};
-  if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_pyr + lay.off[l], dims, strides, box, es,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return cudaErrorNotSupported;
+  CUtensorMap map;  // box = the tile's source region
+  cudaError_t e = encode_level_map(&map, d_pyr, lay, l, first_slot + n_frames, kPdSrcW, 2 * tile_h + 3);
+  if (e != cudaSuccess) return e;
   dim3 grid((dw + kPdTileW - 1) / kPdTileW, (dh + tile_h - 1) / tile_h, n_frames);
 #define SVC_PYR_LAUNCH(RPT)                                                                        \
   pyr_down_kernel<RPT><<<grid, block, 0, st>>>(map, d_pyr, lay.slot_bytes, first_slot, lay.w[l],   \
@@ -346,6 +515,43 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
   else SVC_PYR_LAUNCH(2);
 #undef SVC_PYR_LAUNCH
   return cudaGetLastError();
+}
+
+// levels src_level+1 and src_level+2 in one launch (pyr_down2_kernel)
+static cudaError_t launch_pyr_down2(uint8_t* d_pyr, const PyrLayout& lay, uint32_t src_level, uint32_t first_slot,
+                                    uint32_t n_frames, cudaStream_t st) {
+  const uint32_t l = src_level;
+  CUtensorMap map;
+  cudaError_t e = encode_level_map(&map, d_pyr, lay, l, first_slot + n_frames, kF0BoxW, kF0BoxH);
+  if (e != cudaSuccess) return e;
+  dim3 grid((lay.w[l + 2] + kF2TileW - 1) / kF2TileW, (lay.h[l + 2] + kF2TileH - 1) / kF2TileH, n_frames);
+  pyr_down2_kernel<<<grid, kFusedThreads, 0, st>>>(map, d_pyr, lay.slot_bytes, first_slot, lay.w[l], lay.h[l],
+                                                   lay.off[l + 1], lay.w[l + 1], lay.h[l + 1], lay.pitch[l + 1],
+                                                   lay.off[l + 2], lay.w[l + 2], lay.h[l + 2], lay.pitch[l + 2]);
+  return cudaGetLastError();
+}
+
+// All levels 1 .. L-1 of slots first_slot .. first_slot+n_frames-1 from their level 0: level 0 -> 1
+// on the throughput kernel, the smaller levels two at a time.
+cudaError_t launch_pyr_levels(uint8_t* d_pyr, const PyrLayout& lay, uint32_t first_slot, uint32_t n_frames,
+                              cudaStream_t st, int* n_launches) {
+  if (n_frames == 0) return cudaSuccess;
+  uint32_t l = 0;
+  while (l + 1 < lay.levels) {
+    cudaError_t e;
+    const bool pair = l >= 1 && l + 2 < lay.levels && lay.w[l + 1] >= 4 && lay.h[l + 1] >= 4 &&
+                      lay.w[l] >= 4 && lay.h[l] >= 4 && n_frames <= 65535;
+    if (pair) {
+      e = launch_pyr_down2(d_pyr, lay, l, first_slot, n_frames, st);
+      l += 2;
+    } else {
+      e = launch_pyr_down(d_pyr, lay, l, first_slot, n_frames, st);
+      l += 1;
+    }
+    if (e != cudaSuccess) return e;
+    if (n_launches) *n_launches += 1;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace svc

@@ -332,7 +332,7 @@ int svc_y_pyramid(const uint8_t* bgr, uint32_t frame_w, uint32_t frame_h, uint32
   if (rc) return rc;
   CU(cudaMemcpyAsync(in.p, bgr, in_bytes, cudaMemcpyHostToDevice, st));
   CU(launch_bgr_to_y(in.as<uint8_t>(), frame_w, frame_h, pyr.as<uint8_t>(), lay, 0, 1, st));
-  for (uint32_t l = 0; l + 1 < level_count; ++l) CU(launch_pyr_down(pyr.as<uint8_t>(), lay, l, 0, 1, st));
+  CU(launch_pyr_levels(pyr.as<uint8_t>(), lay, 0, 1, st, nullptr));
   for (uint32_t l = 0; l < level_count; ++l)
     CU(cudaMemcpy2DAsync(out_levels[l], lay.w[l], pyr.as<uint8_t>() + lay.off[l], lay.pitch[l],
                          lay.w[l], lay.h[l], cudaMemcpyDeviceToHost, st));
@@ -687,10 +687,7 @@ int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, flo
 
   // ---- motion stream, part 2: pyramid levels 1.. and the search
   CU(cudaStreamWaitEvent(s->s_aux, s->ev_y, 0));
-  for (uint32_t l = 0; l + 1 < s->lay.levels; ++l) {
-    CU(launch_pyr_down(pyr, s->lay, l, first_slot, m, s->s_aux));
-    nl += 1;
-  }
+  CU(launch_pyr_levels(pyr, s->lay, first_slot, m, s->s_aux, &nl));
   if (n_enc && (d_mv || d_mad)) {
     HbmaParams p{};
     p.pyr = pyr;
@@ -1080,10 +1077,7 @@ int svc_session_run_stage(svc_session* s, int stage, const uint8_t* d_frames, ui
       s->have_prev = false;  // slots of array 0 are overwritten: the encode sequence starts over
       CU(launch_bgr_to_y(d_frames, s->cfg.frame_w, s->cfg.frame_h, s->d_pyr, s->lay, 1, n_frames, s->stream));
       nl += 1;
-      for (uint32_t l = 0; l + 1 < s->lay.levels; ++l) {
-        CU(launch_pyr_down(s->d_pyr, s->lay, l, 1, n_frames, s->stream));
-        nl += 1;
-      }
+      CU(launch_pyr_levels(s->d_pyr, s->lay, 1, n_frames, s->stream, &nl));
       break;
     }
     case SVC_STAGE_HBMA: {
@@ -1130,10 +1124,7 @@ int svc_session_run_stage(svc_session* s, int stage, const uint8_t* d_frames, ui
     }
     case SVC_STAGE_PYR_DOWN: {
       s->have_prev = false;
-      for (uint32_t l = 0; l + 1 < s->lay.levels; ++l) {
-        CU(launch_pyr_down(s->d_pyr, s->lay, l, 1, n_frames, s->stream));
-        nl += 1;
-      }
+      CU(launch_pyr_levels(s->d_pyr, s->lay, 1, n_frames, s->stream, &nl));
       break;
     }
     default:

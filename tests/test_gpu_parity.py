@@ -34,6 +34,37 @@ def test_y_pyramid_vs_oracle(gpu, oracle, w, h, L, B):
         assert np.array_equal(got[l], exp[l]), l
 
 
+@pytest.mark.parametrize("w,h,L", [(1920, 1080, 4), (3840, 2160, 4), (416, 240, 4), (400, 232, 4), (208, 120, 5),
+                                   (1000, 600, 5), (520, 264, 4), (64, 48, 4), (56, 40, 4), (2048, 1024, 6),
+                                   (776, 392, 4), (32, 32, 4), (48, 16, 3)])
+def test_y_pyramid_fused_upper_levels_vs_oracle(gpu, oracle, w, h, L):
+    """Levels above 1 come two per launch (pyr_down2_kernel): full and partial tiles in both directions,
+    REFLECT_101 at the border of BOTH levels, regions larger than the level, 5 and 6 levels (two fused
+    launches / a fused and a single one), frames too small for the fused kernel."""
+    rng = np.random.default_rng(w * 31 + h + L)
+    bgr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    bgr[: h // 3, : w // 3] = 255  # saturated corner: the rounding of each level matters
+    pw, ph = oracle.padded_dim(w, 16, L), oracle.padded_dim(h, 16, L)
+    got = gpu.y_pyramid(bgr, pw, ph, L)
+    exp = oracle.y_pyramid(bgr, pw, ph, L)
+    for l in range(L):
+        assert np.array_equal(got[l], exp[l]), l
+
+
+def test_y_pyramid_fused_levels_in_a_batch(gpu, oracle):
+    """The session path: pyramids of a whole batch (slot stride, first_slot = 1) feed the search."""
+    w, h, n = 432, 248, 7
+    frames = SyntheticSequence(w, h, n, seed=77).frames()
+    for L, R in ((4, 8), (5, 16)):
+        with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, mv_search_range=R, pyr_lvl_count=L, max_batch=4)) as s:
+            mv, mad, _ = s.encode(frames, want_stream=False)
+            pw, ph = s.padded_w, s.padded_h
+        pyr = [oracle.y_pyramid(f, pw, ph, L) for f in frames]
+        for i in range(1, n):
+            emv, emad = oracle.hbma(pyr[i - 1], pyr[i], R)
+            assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad), (L, i)
+
+
 # ---------------------------------------------------------------- K2: motion
 def test_hbma_golden_default(gpu):
     g = load_golden("small_default.npz")
