@@ -49,6 +49,7 @@ def parse():
                     help="input frames in the CPU baseline sample (default 0: the whole --frames workload, "
                          "about 25 core-seconds for 300 frames of 1080p)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity check of the measured outputs")
+    ap.add_argument("--host-chunk", type=int, default=0, help="frames per stage of the host-path pipeline (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sad", action="store_true", help="skip the SAD-roofline side measurement (R=32/64, L=1)")
@@ -389,7 +390,8 @@ def run_ours(a):
     ts = torch.cuda.Stream()
     sess = svc.Session(svc.SessionConfig(frame_w=W, frame_h=H, mv_search_range=a.search_range,
                                          pyr_lvl_count=a.levels, device=local,
-                                         max_batch=a.batch, cuda_stream=ts.cuda_stream))
+                                         max_batch=a.batch, cuda_stream=ts.cuda_stream,
+                                         host_chunk_frames=a.host_chunk))
     mvn = sess.mv_field_w * sess.mv_field_h
     fin, fst = sess.frame_in_bytes, sess.frame_stream_bytes
 

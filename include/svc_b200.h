@@ -161,6 +161,9 @@ typedef struct svc_session_config {
    * pick for a configuration.  SVC_HBMA_FAMILY_AUTO (0) = fastest kernel for the configuration.
    * A caller compiled against the older struct (struct_size without this field) gets AUTO. */
   uint32_t hbma_kernel_family;
+  /* Host path (svc_session_encode): frames per pipeline stage of H2D | kernels | D2H (0 = default 16).
+   * PCIe-bound: small stages keep the three engines overlapped and the exposed head / tail short. */
+  uint32_t host_chunk_frames;
 } svc_session_config;
 
 #define SVC_HBMA_FAMILY_AUTO 0u

@@ -46,6 +46,8 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
                             uint32_t src_level, uint32_t first_slot,
                             uint32_t n_frames, cudaStream_t st);
 
+// device-to-device copy of one pyramid slot on the SMs (not on a copy engine)
+cudaError_t launch_copy_slot(uint8_t* dst, const uint8_t* src, size_t bytes, cudaStream_t st);
 // every level above 0 of n_frames slots (level 0 -> 1, then the smaller levels two per launch)
 cudaError_t launch_pyr_levels(uint8_t* d_pyr, const PyrLayout& lay, uint32_t first_slot,
                               uint32_t n_frames, cudaStream_t st, int* n_launches);

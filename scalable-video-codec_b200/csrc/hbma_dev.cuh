@@ -47,9 +47,18 @@ inline bool encode_box(CUtensorMap* m, const uint8_t* base, uint32_t w, uint32_t
 }
 
 
+struct EbmaMaps {
+  CUtensorMap t;  // tracked window box of one level
+  CUtensorMap a;  // anchor block / anchor tile box of the same level
+};
+
+// mid ranges (r = 3..8), one level per launch, windows realigned in registers (k_hbma_rs.cu)
+struct HbmaParams;
+bool rs_level_supported(const HbmaParams& p);
+cudaError_t launch_rs_level(const HbmaParams& p, uint32_t lvl, bool top, cudaStream_t st);
+
 // large-range 16x16 search with pooled work items and pre-shifted window copies (k_hbma_pool.cu);
 // returns false when the configuration is outside its limits (the caller picks another kernel)
-struct HbmaParams;
 // (*extra_launches += launches beyond the first, for the level-synchronous path)
 bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int* extra_launches);
 // hbma_tile_kernel (k_hbma.cu) over the three coarsest levels of a 5-level pyramid (r = 3, 4): vectors

@@ -493,11 +493,6 @@ __device__ __forceinline__ void tile_build_copies(uint8_t* smem, const int total
 // one shared window per tile of NBX horizontally adjacent blocks, see TileGeomE.  Same work
 // items, same argmin, same zero-vector rule as pool_level's top level.
 // ---------------------------------------------------------------------------------------
-struct EbmaMaps {
-  CUtensorMap t;  // window box: PT x (16 + 2r)
-  CUtensorMap a;  // anchor tile box: 16 NBX x 16
-};
-
 // B = block size at the searched level `lvl` (16 >> lvl): 16 / level 0 for L = 1; the top level of a
 // deeper pyramid otherwise, whose vector and MAD it leaves in p.mv / p.mad for hbma_refine_kernel.
 template <int RC, int NBX, int NDY, int THREADS, int MINB, int B = 16>
@@ -1075,15 +1070,21 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int
   // r <= 4: hbma_tile_kernel, or (5 levels, r = 3, 4: the reach does not fit a tile) the hybrid below
   if (!force && p.bw == 16 && p.bh == 16 && L == 5 && (r == 3 || r == 4) && p.mv && p.mad &&
       p.n_frames <= 65535 && (uint64_t)p.mvw * p.mvh * p.n_frames <= 0x7fffffffull) {
-    // tile kernel over levels 4..2, then one refinement launch per remaining level
+    // tile kernel over levels 4..2, then one refinement launch per remaining level (k_hbma_rs.cu)
     *err = launch_tile_upper3(p, st);
-    if (*err == cudaSuccess) *err = launch_refine<8, 7, 9, 128, 4, 8>(p, 1, st);
-    if (*err == cudaSuccess) *err = launch_refine<8, 7, 9, 128, 4, 16>(p, 0, st);
+    if (*err == cudaSuccess) *err = launch_rs_level(p, 1, false, st);
+    if (*err == cudaSuccess) *err = launch_rs_level(p, 0, false, st);
     if (extra_launches) *extra_launches += 2;
     return true;
   }
   if (p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > (L == 1 ? 112u : 64u)) return false;
   if ((uint64_t)p.mvw * p.mvh * p.n_frames > 0x7fffffffull) return false;
+  if (r <= 8 && !force && rs_level_supported(p)) {
+    // windows of at most 17 x 17 candidates: one launch per level, realigned in registers (k_hbma_rs.cu)
+    for (int l = (int)L - 1; l >= 0 && *err == cudaSuccess; --l) *err = launch_rs_level(p, (uint32_t)l, l == (int)L - 1, st);
+    if (extra_launches) *extra_launches += (int)L - 1;  // the caller counts one
+    return true;
+  }
   if (L >= 2 && r <= 32 && p.mv && p.mad && !force) {
     // one launch per level; <range class, candidate rows per item, blocks per CTA and CTAs per SM of
     // the 16x16 refinement level>

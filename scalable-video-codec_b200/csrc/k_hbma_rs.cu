@@ -1,0 +1,341 @@
+// k_hbma_rs.cu -- K2, mid search ranges (16x16 motion blocks, top-level range r = 3..8): ONE pyramid
+// level per launch with the candidate windows in shared memory exactly as TMA delivers them
+// ("rs" = register shift; the level-synchronous path of k_hbma_pool.cu launches these).
+//
+// Same arithmetic and scan-order rules as k_hbma.cu (reference libs/motion.cpp:268-465, 691-749):
+// clamped windows (:297-310, 375-385), "<=" / last-minimum + all-updates => zero vector at the top
+// level (:312-337), strict "<" against the MAD carried from the coarser level below it (:401-405),
+// the carried vector doubled between levels (:459).
+//
+// Why another layout.  For windows of at most 17 x 17 candidates the pooled kernels of
+// k_hbma_pool.cu spend more time around the SAD loop than in it (ncu, r = 8, 16x16 level: 59 % of
+// the instructions are VABSDIFF4, the ALU pipe is 64 % busy, a CTA waits on its TMA round trip,
+// builds three shifted copies of every window behind a block-wide barrier, and only three 128-thread
+// CTAs fit an SM next to 71 KB of window copies).  Here nothing is rebuilt:
+//   * a work item is 4 candidate columns of ONE byte phase (columns p, p+4, p+8, p+12 of the window)
+//     times a chunk of <= 6 candidate rows.  The four columns read the same aligned words of a window
+//     row, so one funnel shift per word serves all four: 7 SHF per row against 16 VABSDIFF4 per row
+//     and candidate row -- the realignment costs ~9 % of the SAD work and needs no copies, no build
+//     phase and no barrier; the 17th column of a full window forms its own 1-column items;
+//   * a window is 48 x (B + 2r) bytes (1.6 KB for the 16x16 level instead of 9.9 KB with copies), so
+//     8 blocks per 128-thread CTA need 15 KB and the register file, not shared memory, limits the
+//     CTAs per SM (4 CTAs: while one waits for its windows three others keep the ALU pipe busy);
+//   * items map to lanes statically (block = lane / 12 ..): no pooled item decode;
+//   * the anchor block lives in registers (B*B/4), each item keeps 4 x 6 running SADs.
+#include <float.h>
+
+#include "common.cuh"
+#include "hbma_dev.cuh"
+
+namespace svc {
+
+namespace {
+
+constexpr int kRsPT = 48;  // window pitch = TMA box width: 15 (16-byte origin) + 2*8 + 16 + 1 word of shift slack
+
+struct RsLv {        // one motion block at this level
+  int x0, y0;        // origin of the clamped candidate window
+  int ncx, ncy;      // its size (0 x 0: no block)
+  int csz;           // candidate rows per chunk
+  int sxb, aoff;     // byte offset of x0 inside the TMA box; of the anchor block inside its box
+};
+
+// NC candidate columns of one byte phase (4 bytes apart) x NDY candidate rows of a BxB anchor block.
+// `trow` = first window row of the chunk at the aligned word that holds the first column, `sh` = 8 *
+// (byte offset of that column inside the word).  Streams B + NDY - 1 window rows once.
+template <int B, int NC, int NDY>
+__device__ __forceinline__ void rs_item(const uint8_t* __restrict__ trow, const uint32_t sh,
+                                        const uint8_t* __restrict__ ablk, uint32_t (&acc)[NC][NDY]) {
+  constexpr int NW = B >= 4 ? B / 4 : 1;      // words per block row
+  constexpr uint32_t MASK = B >= 4 ? 0xffffffffu : (B == 2 ? 0xffffu : 0xffu);
+  constexpr int NS = NW + NC - 1;             // shifted words per row: column i uses s[i .. i+NW-1]
+  uint32_t a[B][NW];
+#pragma unroll
+  for (int k = 0; k < B; ++k) {
+    const uint8_t* q = ablk + k * 16;
+    if constexpr (B == 16) {
+      const uint4 v = *reinterpret_cast<const uint4*>(q);
+      a[k][0] = v.x; a[k][1] = v.y; a[k][2] = v.z; a[k][3] = v.w;
+    } else if constexpr (B == 8) {
+      const uint2 v = *reinterpret_cast<const uint2*>(q);
+      a[k][0] = v.x; a[k][1] = v.y;
+    } else if constexpr (B == 4) {
+      a[k][0] = *reinterpret_cast<const uint32_t*>(q);
+    } else if constexpr (B == 2) {
+      a[k][0] = *reinterpret_cast<const uint16_t*>(q);
+    } else {
+      a[k][0] = *q;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < B + NDY - 1; ++t) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(trow + t * kRsPT);
+    uint32_t s[NS + 1];
+#pragma unroll
+    for (int k = 0; k <= NS; ++k) s[k] = q[k];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) s[k] = __funnelshift_r(s[k], s[k + 1], sh) & MASK;
+#pragma unroll
+    for (int dyi = 0; dyi < NDY; ++dyi) {
+      const int ar = t - dyi;
+      if (ar >= 0 && ar < B) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+#pragma unroll
+          for (int k = 0; k < NW; ++k) acc[i][dyi] = sad4_acc(s[i + k], a[ar][k], acc[i][dyi]);
+      }
+    }
+  }
+}
+
+// keys of one item into the block's running minimum (+ the SADs themselves at the top level)
+template <int NC, int NDY, bool TOP>
+__device__ __forceinline__ void rs_commit(const uint32_t (&acc)[NC][NDY], const RsLv& v, const int col0,
+                                          const int dy0, uint32_t* best, uint16_t* sads) {
+  const int ndy = min(v.csz, v.ncy - dy0);
+  uint32_t key = 0xffffffffu;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int col = col0 + 4 * i;
+    if (col < v.ncx) {
+#pragma unroll
+      for (int d = 0; d < NDY; ++d) {
+        if (d < ndy) {
+          const uint32_t idx = (uint32_t)((dy0 + d) * v.ncx + col);  // scan order inside the clamped window
+          if (TOP) {
+            sads[idx] = (uint16_t)acc[i][d];
+            key = min(key, acc[i][d] * 65536u + (0xffffu - idx));  // "<=": the last minimum wins
+          } else {
+            key = min(key, acc[i][d] * 65536u + idx);              // "<": the first minimum wins
+          }
+        }
+      }
+    }
+  }
+  if (key != 0xffffffffu) atomicMin(best, key);
+}
+
+template <int B, int NDY, int NB>
+struct RsGeom {
+  static constexpr int ROWS = B + 16 + NDY;                       // + slack rows a short last chunk streams
+  static constexpr int WIN = (kRsPT * ROWS + 127) & ~127;
+  static constexpr int ANC = (16 * B + 127) & ~127;               // anchor box: 16 x B bytes
+  static constexpr int BLK = WIN + ANC;
+  static constexpr int SADS = 17 * 17 * 2 + 2;                    // u16 per candidate (top level only)
+  static constexpr int OFF_SADS = NB * BLK;
+};
+
+// B: block size at level `lvl`; TOP: exhaustive top level (EstimateMotionExhaustiveSearch semantics) or
+// refinement of the vector / MAD found in p.mv / p.mad; NC columns per item, NDY rows per chunk, NCH
+// chunks per window, NB blocks per CTA; LAST: a full window has a 17th column (r = 8), searched by
+// 1-column items on an extra warp.
+template <int B, bool TOP, int NC, int NDY, int NCH, int NB, bool LAST, int MINB>
+__global__ void __launch_bounds__(NB * 4 * NCH + (LAST ? 32 : 0), MINB)
+hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ HbmaParams p, const int lvl) {
+  using G = RsGeom<B, NDY, NB>;
+  constexpr int MAIN = NB * 4 * NCH;
+  static_assert(MAIN % 32 == 0, "main items must fill whole warps");
+  static_assert(!LAST || NB * NCH <= 32, "last-column items must fit one warp");
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ RsLv sLv[NB];
+  __shared__ uint32_t sBest[NB], sViol[NB];
+  const int tid = threadIdx.x;
+  const uint32_t per_frame = p.mvw * p.mvh;
+  const uint32_t n_blocks = per_frame * p.n_frames;  // < 2^31 (checked on the host)
+  const int r = (int)p.r;
+  const int box_h = B + 2 * r;
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_addr), "r"(NB));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // ---- thread j < NB owns motion block j of this CTA: window geometry, TMA loads -------------
+  int mx = 0, my = 0, x0 = 0, y0 = 0, ncx = 1, ax = 0, ay = 0;
+  float cur = FLT_MAX;
+  uint32_t gb = 0;
+  bool own = false;
+  if (tid < NB) {
+    gb = blockIdx.x * NB + tid;
+    own = gb < n_blocks;
+    RsLv v{};
+    if (own) {
+      const uint32_t f = gb / per_frame, bi = gb - f * per_frame;
+      const int bx = (int)(bi % p.mvw), by = (int)(bi / p.mvw);
+      if (!TOP) {
+        const float2 m = p.mv[gb];  // integer valued (libs/motion.cpp:326-327, 403-404)
+        cur = p.mad[gb];
+        mx = 2 * (int)m.x;          // motion_field *= 2 between levels (libs/motion.cpp:459)
+        my = 2 * (int)m.y;
+      }
+      const int fw = (int)p.lay.w[lvl], fh = (int)p.lay.h[lvl];
+      ax = bx * B;
+      ay = by * B;
+      const int cx = ax + mx, cy = ay + my;
+      x0 = max(0, cx - r);
+      y0 = max(0, cy - r);
+      const int x1 = min(fw - B + 1, cx + r + 1), y1 = min(fh - B + 1, cy + r + 1);
+      ncx = x1 - x0;
+      const int ncy = y1 - y0;
+      v.x0 = x0; v.y0 = y0; v.ncx = ncx; v.ncy = ncy;
+      v.csz = (ncy + NCH - 1) / NCH;
+      v.sxb = x0 & 15;
+      v.aoff = ax & 15;
+      sLv[tid] = v;
+      sBest[tid] = 0xffffffffu;
+      sViol[tid] = 0u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                   "r"((uint32_t)(kRsPT * box_h + 16 * B)) : "memory");
+      uint8_t* blk = smem + tid * G::BLK;
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(blk)), "l"(&maps.t), "r"(x0 & ~15), "r"(y0), "r"((int)f),
+          "r"(bar_addr) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(blk + G::WIN)), "l"(&maps.a), "r"(ax & ~15), "r"(ay),
+          "r"((int)f + 1), "r"(bar_addr) : "memory");
+    } else {
+      sLv[tid] = v;
+      sBest[tid] = 0xffffffffu;
+      sViol[tid] = 0u;
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+    }
+  }
+  {  // windows landed; sLv / sBest published (arrive = release, wait = acquire)
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar_addr), "r"(0u) : "memory");
+    }
+  }
+  // ---- work items: static lane -> (block, byte phase, chunk) ----------------------------------
+  if (tid < MAIN) {
+    const int j = tid / (4 * NCH), rem = tid - j * (4 * NCH);
+    const int ph = rem / NCH, c = rem - ph * NCH;
+    const RsLv v = sLv[j];
+    const int dy0 = c * v.csz;
+    if (ph < v.ncx && dy0 < v.ncy) {
+      const uint8_t* blk = smem + j * G::BLK;
+      const int sx = v.sxb + ph;
+      uint32_t acc[NC][NDY];
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int d = 0; d < NDY; ++d) acc[i][d] = 0;
+      rs_item<B, NC, NDY>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, blk + G::WIN + v.aoff, acc);
+      rs_commit<NC, NDY, TOP>(acc, v, ph, dy0, &sBest[j],
+                              reinterpret_cast<uint16_t*>(smem + G::OFF_SADS) + j * (G::SADS / 2));
+    }
+  } else if (LAST) {
+    const int l = tid - MAIN;
+    const int j = l / NCH, c = l - j * NCH;
+    if (j < NB) {
+      const RsLv v = sLv[j];
+      const int dy0 = c * v.csz;
+      if (v.ncx > 4 * NC && dy0 < v.ncy) {  // the window has a column 4*NC (= 16)
+        const uint8_t* blk = smem + j * G::BLK;
+        const int sx = v.sxb + 4 * NC;
+        uint32_t acc[1][NDY];
+#pragma unroll
+        for (int d = 0; d < NDY; ++d) acc[0][d] = 0;
+        rs_item<B, 1, NDY>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, blk + G::WIN + v.aoff, acc);
+        rs_commit<1, NDY, TOP>(acc, v, 4 * NC, dy0, &sBest[j],
+                               reinterpret_cast<uint16_t*>(smem + G::OFF_SADS) + j * (G::SADS / 2));
+      }
+    }
+  }
+  __syncthreads();
+  if (TOP) {
+    // "every candidate updated the minimum" <=> the SADs never increase along the scan order of the
+    // clamped window (libs/motion.cpp:312-337)
+    for (int e = tid; e < NB * 17 * 17; e += blockDim.x) {
+      const int j = e / (17 * 17), i = e - j * (17 * 17);
+      const int n = sLv[j].ncx * sLv[j].ncy;
+      if (i >= 1 && i < n) {
+        const uint16_t* s = reinterpret_cast<const uint16_t*>(smem + G::OFF_SADS) + j * (G::SADS / 2);
+        if (s[i] > s[i - 1]) sViol[j] = 1u;
+      }
+    }
+    __syncthreads();
+  }
+  if (own) {  // tid < NB
+    const uint32_t best = sBest[tid];
+    const float m = (float)(best >> 16) * (1.0f / (float)(B * B));
+    if (TOP) {
+      const int idx = (int)(0xffffu - (best & 0xffffu));
+      const bool any_viol = sViol[tid] != 0u;
+      p.mv[gb] = any_viol ? make_float2((float)(x0 + idx % ncx - ax), (float)(y0 + idx / ncx - ay))
+                          : make_float2(0.f, 0.f);
+      p.mad[gb] = m;
+    } else {
+      // strict "<" against the MAD carried from the coarser level (libs/motion.cpp:401-405)
+      if (best != 0xffffffffu && m < cur) {
+        const int idx = (int)(best & 0xffffu);
+        cur = m;
+        mx = x0 + idx % ncx - ax;
+        my = y0 + idx / ncx - ay;
+      }
+      p.mv[gb] = make_float2((float)mx, (float)my);
+      p.mad[gb] = cur;
+    }
+  }
+}
+
+template <int B, bool TOP, int NC, int NDY, int NCH, int NB, bool LAST, int MINB>
+cudaError_t launch_rs(const HbmaParams& p, uint32_t lvl, cudaStream_t st) {
+  using G = RsGeom<B, NDY, NB>;
+  constexpr int SMEM = G::OFF_SADS + (TOP ? NB * G::SADS : 0);
+  constexpr int THREADS = NB * 4 * NCH + (LAST ? 32 : 0);
+  EbmaMaps maps;
+  const uint32_t n_slots = p.n_frames + 1;
+  const uint8_t* base = p.pyr + p.lay.off[lvl];
+  if (!encode_box(&maps.t, base, p.lay.w[lvl], p.lay.h[lvl], p.lay.pitch[lvl], p.lay.slot_bytes, n_slots, kRsPT,
+                  B + 2 * p.r) ||
+      !encode_box(&maps.a, base, p.lay.w[lvl], p.lay.h[lvl], p.lay.pitch[lvl], p.lay.slot_bytes, n_slots, 16, B))
+    return cudaErrorNotSupported;
+  auto kern = hbma_rs_kernel<B, TOP, NC, NDY, NCH, NB, LAST, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  if (e != cudaSuccess) return e;
+  const uint64_t n_blocks = (uint64_t)p.mvw * p.mvh * p.n_frames;
+  kern<<<(uint32_t)((n_blocks + NB - 1) / NB), THREADS, SMEM, st>>>(maps, p, (int)lvl);
+  return cudaGetLastError();
+}
+
+// range classes: r = 5..8 -> windows up to 17 x 17: 4 columns x 6 rows per item, 3 chunks, 8 blocks per CTA
+// and the 17th column on a fifth warp...; r = 3, 4 -> up to 9 x 9: 3 columns x 5 rows, 2 chunks, 16 blocks.
+template <int B, bool TOP>
+cudaError_t launch_rs_class(const HbmaParams& p, uint32_t lvl, cudaStream_t st) {
+  constexpr int MINB = B == 16 ? 4 : 6;
+  if (p.r >= 5) return launch_rs<B, TOP, 4, 6, 3, 8, true, MINB>(p, lvl, st);
+  return launch_rs<B, TOP, 3, 5, 2, 16, false, MINB>(p, lvl, st);
+}
+
+}  // namespace
+
+bool rs_level_supported(const HbmaParams& p) {
+  return p.bw == 16 && p.bh == 16 && p.r >= 3 && p.r <= 8 && p.mv && p.mad && p.lay.levels <= 5 &&
+         (uint64_t)p.mvw * p.mvh * p.n_frames <= 0x7fffffffull;
+}
+
+cudaError_t launch_rs_level(const HbmaParams& p, uint32_t lvl, bool top, cudaStream_t st) {
+  const int B = 16 >> lvl;
+#define SVC_RS_CASE(BB)                                                          \
+  case BB:                                                                       \
+    return top ? launch_rs_class<BB, true>(p, lvl, st) : launch_rs_class<BB, false>(p, lvl, st);
+  switch (B) {
+    SVC_RS_CASE(16)
+    SVC_RS_CASE(8)
+    SVC_RS_CASE(4)
+    SVC_RS_CASE(2)
+    SVC_RS_CASE(1)
+  }
+#undef SVC_RS_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace svc

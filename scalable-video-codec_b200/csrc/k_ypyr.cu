@@ -12,6 +12,8 @@
 // All arithmetic is integer and bit-exact with OpenCV's 8-bit paths.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace svc {
@@ -299,14 +301,16 @@ pyr_down_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restrict
 // level: level l in the TMA tile as in pyr_down_kernel, level l+1 by reflecting the out-of-image part
 // of the region inside shared memory before phase 2.
 // ---------------------------------------------------------------------------
-constexpr int kF2TileW = 24, kF2TileH = 8;                    // level l+2 tile
-constexpr int kF1W = 2 * kF2TileW + 3, kF1H = 2 * kF2TileH + 3;  // 51 x 19: level l+1 region
+constexpr int kF2TileW = 24, kF2TileH = 16;                   // level l+2 tile
+constexpr int kF1W = 2 * kF2TileW + 3, kF1H = 2 * kF2TileH + 3;  // 51 x 35: level l+1 region
 constexpr int kF1Groups = (kF1W + 3) / 4;                     // 13 groups of 4 columns
-constexpr int kF1Rpt = 2, kF1Strips = (kF1H + kF1Rpt - 1) / kF1Rpt;  // 10 strips of 2 rows
-constexpr int kF0BoxW = 144, kF0BoxH = 2 * kF1H + 3;          // 144 x 41: TMA box of level l
-constexpr int kF0Rows = 2 * kF1Rpt * kF1Strips + 3;           // 43: rows the phase-1 threads may touch
+constexpr int kF1Rpt = 4, kF1Strips = (kF1H + kF1Rpt - 1) / kF1Rpt;  // 9 strips of 4 rows
+constexpr int kF0BoxW = 144, kF0BoxH = 2 * kF1H + 3;          // 144 x 73: TMA box of level l
+constexpr int kF0Rows = 2 * kF1Rpt * kF1Strips + 3;           // 75: rows the phase-1 threads may touch
 constexpr int kF1Pitch = 64;                                   // level l+1 region: column j at byte j + 2
-constexpr int kFusedThreads = 160;
+constexpr int kF2Rpt = 2;                                      // phase 2: level l+2 rows per thread
+constexpr int kFusedThreads = 128;
+static_assert((kF2TileW / 4) * (kF2TileH / kF2Rpt) <= kFusedThreads, "phase 2 does not fit the CTA");
 static_assert(kF1Groups * kF1Strips <= kFusedThreads, "phase 1 does not fit the CTA");
 static_assert(8 * (kF1Groups - 1) + 4 + 20 <= kF0BoxW, "phase 1 reads past the box");
 
@@ -371,7 +375,7 @@ pyr_down2_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restric
       __syncthreads();
     }
   }
-  // ---- phase 1: level l+1 region, 4 columns x 2 rows per thread --------------------------------
+  // ---- phase 1: level l+1 region, 4 columns x 4 rows per thread --------------------------------
   if (threadIdx.x < kF1Groups * kF1Strips) {
     const int g = threadIdx.x % kF1Groups, sidx = threadIdx.x / kF1Groups;
     // region column j = 4g + i reads tile columns 2j + 10 .. 2j + 14 = (8g + 4) + 6 + 2i ..
@@ -420,15 +424,17 @@ pyr_down2_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restric
       __syncthreads();
     }
   }
-  // ---- phase 2: level l+2 tile, 4 columns x 1 row per thread ------------------------------------
-  if (threadIdx.x < (kF2TileW / 4) * kF2TileH) {
-    const int g = threadIdx.x % (kF2TileW / 4), row = threadIdx.x / (kF2TileW / 4);
-    const int ox = x0 + 4 * g, oy = y0 + row;
+  // ---- phase 2: level l+2 tile, 4 columns x 2 rows per thread -----------------------------------
+  if (threadIdx.x < (kF2TileW / 4) * (kF2TileH / kF2Rpt)) {
+    const int g = threadIdx.x % (kF2TileW / 4), sidx = threadIdx.x / (kF2TileW / 4);
+    const int ox = x0 + 4 * g, oy = y0 + kF2Rpt * sidx;
     if (ox < (int)w2 && oy < (int)h2) {
       // output q = 4g + i reads region columns 2q .. 2q + 4 = bytes 2q + 2 .. = (8g - 4) + 6 + 2i ..
-      uint32_t px[1];
-      pyr_down_rows<1, kF1Pitch, false>(t1 + (2 * row) * kF1Pitch + 8 * g - 4, px);
-      *reinterpret_cast<uint32_t*>(slot + off2 + (uint64_t)oy * pitch2 + ox) = px[0];
+      uint32_t px[kF2Rpt];
+      pyr_down_rows<kF2Rpt, kF1Pitch, false>(t1 + (2 * kF2Rpt * sidx) * kF1Pitch + 8 * g - 4, px);
+#pragma unroll
+      for (int y = 0; y < kF2Rpt; ++y)
+        if (oy + y < (int)h2) *reinterpret_cast<uint32_t*>(slot + off2 + (uint64_t)(oy + y) * pitch2 + ox) = px[y];
     }
   }
 }
@@ -456,6 +462,22 @@ pyr_down_small_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t f
     acc += wv * hsum;
   }
   slot[dst_off + (uint64_t)oy * dpitch + ox] = (uint8_t)((acc + 128) >> 8);
+}
+
+// Hand-over of one pyramid slot (the previous frame, libs/encoder.cpp:661-663) as a kernel: a
+// cudaMemcpyAsync D2D may be queued on the copy engine that is busy with a 400 MB device-to-host
+// transfer of the host path, which would stall the whole motion stream behind it.
+__global__ void __launch_bounds__(256) copy_slot_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+cudaError_t launch_copy_slot(uint8_t* dst, const uint8_t* src, size_t bytes, cudaStream_t st) {
+  // slots are 256-byte multiples at 256-byte aligned offsets of a cudaMalloc'd array
+  const size_t n = bytes / 16;
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)kNumSms * 8);
+  copy_slot_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), n);
+  return cudaGetLastError();
 }
 
 typedef CUresult (*PyrEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -659,8 +659,9 @@ int encode_batch_device(svc_session* s, const uint8_t* d_frames, uint32_t m, flo
   // The copy issued by the PREVIOUS batch read the array this batch is about to overwrite.
   if (s->copy_pending) CU(cudaStreamWaitEvent(s->stream, s->ev_copy, 0));
   if (s->have_prev) {
-    CU(cudaMemcpyAsync(pyr, s->d_pyrs[s->prev_array] + (size_t)s->prev_slot * s->lay.slot_bytes,
-                       s->lay.slot_bytes, cudaMemcpyDeviceToDevice, s->s_aux));
+    CU(launch_copy_slot(pyr, s->d_pyrs[s->prev_array] + (size_t)s->prev_slot * s->lay.slot_bytes,
+                        s->lay.slot_bytes, s->s_aux));
+    nl += 1;
     CU(cudaEventRecord(s->ev_copy, s->s_aux));
     s->copy_pending = true;
   }
@@ -884,6 +885,7 @@ int svc_session_create(const svc_session_config* cfg_in, svc_session** out) {
   if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamSynchronize"));
   // (the scratch planes of the generic transform path are allocated on first use, see
   // encode_batch_device / svc_session_run_stage: the fused stream kernels never touch them)
+  if (cfg->host_chunk_frames) s->host_chunk = cfg->host_chunk_frames;
   *out = s;
   return SVC_OK;
 }

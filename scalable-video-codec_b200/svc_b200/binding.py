@@ -39,7 +39,7 @@ class _Cfg(C.Structure):
                 ("mv_search_range", C.c_uint32), ("pyr_lvl_count", C.c_uint32),
                 ("transform_block_w", C.c_uint32), ("transform_block_h", C.c_uint32),
                 ("device", C.c_int32), ("max_batch", C.c_uint32), ("cuda_stream", C.c_void_p),
-                ("hbma_kernel_family", C.c_uint32)]
+                ("hbma_kernel_family", C.c_uint32), ("host_chunk_frames", C.c_uint32)]
 
 
 class _Info(C.Structure):
@@ -374,6 +374,7 @@ class SessionConfig:
     max_batch: int = 0
     cuda_stream: int = 0
     hbma_kernel_family: int = 0  # test hook: HBMA_FAMILY_*
+    host_chunk_frames: int = 0   # frames per H2D | kernels | D2H pipeline stage of encode() (0 = 16)
 
 
 def _addr(x) -> Optional[int]:
@@ -395,7 +396,7 @@ class Session:
         c = _Cfg(C.sizeof(_Cfg), cfg.frame_w, cfg.frame_h, cfg.mv_block_w, cfg.mv_block_h,
                  cfg.mv_search_range, cfg.pyr_lvl_count, cfg.transform_block_w,
                  cfg.transform_block_h, cfg.device, cfg.max_batch, cfg.cuda_stream or None,
-                 cfg.hbma_kernel_family)
+                 cfg.hbma_kernel_family, cfg.host_chunk_frames)
         h = C.c_void_p()
         _check(lib().svc_session_create(C.byref(c), C.byref(h)))
         self._h = h

@@ -5,7 +5,7 @@
 The UNMODIFIED reference (EstimateMotionHierarchical / EstimateMotionExhaustiveSearch through
 oracle/_ref/libref_motion.so, libs/motion.cpp:268-465) is run once on ONE 1080p frame pair of the
 seeded synthetic sequence the sweep uses (tools/sweep_hbma.py: SyntheticSequence(1920, 1080, n,
-seed=1234), frames 1 and 2) for the wide-range configurations that take the scalar reference tens
+seed=1234) with n = 45 = the sweep's --frames-small, frames 1 and 2) for the wide-range configurations that take the scalar reference tens
 of seconds each; tests/test_gpu_parity.py and tools/sweep_hbma.py compare the CUDA kernels against
 this file, so the wide-range rows of the sweep carry a parity bit without re-running the reference.
 """
@@ -24,14 +24,14 @@ from oracle import oracle as O  # noqa: E402
 from svc_b200.synth import SyntheticSequence  # noqa: E402
 
 CONFIGS = [(32, 1), (64, 1), (64, 2), (64, 3), (32, 2)]  # (search range R, pyramid levels L)
-W, H, SEED = 1920, 1080, 1234
+W, H, SEED, NFRAMES = 1920, 1080, 1234, 45  # the generator's later draws depend on the frame count
 
 
 def main():
     assert O.have_ref(), "build oracle/_ref first (make -C oracle)"
-    seq = SyntheticSequence(W, H, 3, seed=SEED)
+    seq = SyntheticSequence(W, H, NFRAMES, seed=SEED)
     f1, f2 = seq.frame(1), seq.frame(2)
-    out = {"width": W, "height": H, "seed": SEED, "pair": np.array([1, 2])}
+    out = {"width": W, "height": H, "seed": SEED, "n_frames": NFRAMES, "pair": np.array([1, 2])}
     for R, L in CONFIGS:
         pw, ph = O.padded_dim(W, 16, L), O.padded_dim(H, 16, L)
         p0, p1 = O.y_pyramid(f1, pw, ph, L), O.y_pyramid(f2, pw, ph, L)

@@ -100,7 +100,7 @@ def test_c3_sweep_wide_range_rows_1080p_vs_reference_golden(gpu, R, L):
     reference) against fields the unmodified reference produced once (make_golden_sweep.py)."""
     g = np.load(SWEEP_GOLDEN)
     w, h = int(g["width"]), int(g["height"])
-    seq = SyntheticSequence(w, h, 3, seed=int(g["seed"]))
+    seq = SyntheticSequence(w, h, int(g["n_frames"]), seed=int(g["seed"]))  # the sweep tool's sequence
     fr = np.stack([seq.frame(1), seq.frame(2)])
     with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, mv_search_range=R, pyr_lvl_count=L, max_batch=2)) as s:
         mv, mad, _ = s.encode(fr, want_stream=False)
@@ -110,7 +110,7 @@ def test_c3_sweep_wide_range_rows_1080p_vs_reference_golden(gpu, R, L):
 
 def test_sweep_golden_is_committed_and_well_formed():
     g = np.load(SWEEP_GOLDEN)
-    assert (int(g["width"]), int(g["height"]), int(g["seed"])) == (1920, 1080, 1234)
+    assert (int(g["width"]), int(g["height"]), int(g["seed"]), int(g["n_frames"])) == (1920, 1080, 1234, 45)
     for R, L in [(32, 1), (64, 1), (64, 2), (64, 3), (32, 2)]:
         mv, mad = g[f"mv_R{R}_L{L}"], g[f"mad_R{R}_L{L}"]
         assert mv.shape == (68, 120, 2) and mad.shape == (68, 120) and mad.dtype == np.float32

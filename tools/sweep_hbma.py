@@ -98,7 +98,8 @@ def main():
                 mad = d_mad.cpu().numpy().reshape(F, sess.mv_field_h, sess.mv_field_w)
                 row["bit_exact_vs_reference"] = bool(np.array_equal(mv[2], rmv) and np.array_equal(mad[2], rmad))
                 row["parity_source"] = "reference run live (oracle/_ref)"
-            elif golden is not None and f"mv_R{R}_L{L}" in golden and (W, H) == (1920, 1080):
+            elif (golden is not None and f"mv_R{R}_L{L}" in golden and
+                  (W, H, F_max) == (int(golden["width"]), int(golden["height"]), int(golden["n_frames"]))):
                 # wide ranges: the scalar reference needs tens of seconds per pair; its output for this very
                 # pair (frames 1, 2 of the seed-1234 sequence) is committed in tests/golden/sweep_1080p.npz
                 mv = d_mv.cpu().numpy().reshape(F, sess.mv_field_h, sess.mv_field_w, 2)
