@@ -557,6 +557,51 @@ def run_ours(a):
             par_out["e2e_host_buffers"] = (h_mv.view(np.float32, (n_enc, sess.mv_field_h, sess.mv_field_w, 2)),
                                            h_mad.view(np.float32, (n_enc, sess.mv_field_h, sess.mv_field_w)),
                                            h_st.view(np.uint8, (n_enc, fst)).__getitem__)
+    # ---------------- copy-only ceiling of the e2e figure, measured in this run ----------------------
+    # The same pinned buffers and byte volumes moved by plain cudaMemcpyAsync on two streams, no kernels
+    # (tools/pcie_probe.py, mode `both`), all ranks at once: what the host <-> device path of this box
+    # delivers at this N.  e2e.frac = e2e / that.
+    if e2e is not None:
+        try:
+            t_in = torch.from_numpy(h_in.array)
+            t_out = torch.from_numpy(h_st.array)
+            C = 16
+            d_ci = torch.empty(2 * C * fin, dtype=torch.uint8, device="cuda")
+            d_co = torch.empty(2 * C * fst, dtype=torch.uint8, device="cuda")
+            s_i, s_o = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def copy_only():
+                k = 0
+                for lo in range(0, F, C):
+                    n = min(C, F - lo)
+                    with torch.cuda.stream(s_i):
+                        d_ci[(k & 1) * C * fin:(k & 1) * C * fin + n * fin].copy_(t_in[lo * fin:(lo + n) * fin], non_blocking=True)
+                    ne = max(0, min(n, n_enc - lo))
+                    if ne:
+                        with torch.cuda.stream(s_o):
+                            t_out[lo * fst:(lo + ne) * fst].copy_(d_co[(k & 1) * C * fst:(k & 1) * C * fst + ne * fst], non_blocking=True)
+                    k += 1
+
+            copy_only()
+            best = None
+            for _ in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                copy_only()
+                torch.cuda.synchronize()
+                dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                best = float(dt.item()) if best is None else min(best, float(dt.item()))
+            ceil_fps = world * n_enc / best
+            e2e["copy_only_ceiling"] = {"value": ceil_fps, "unit": UNIT, "seconds": best,
+                                        "aggregate_gbs": world * (F * fin + n_enc * fst) / best / 1e9,
+                                        "what": "same pinned buffers and bytes, cudaMemcpyAsync H2D || D2H in 16-frame "
+                                                "chunks, no kernels, all ranks at once (max over ranks, best of 3)"}
+            e2e["frac"] = e2e["value"] / ceil_fps
+            del d_ci, d_co
+        except Exception as ex:  # never let the side measurement take the headline line down
+            e2e["copy_only_ceiling"] = {"error": str(ex)[:200]}
     # ---------------- SAD-bound corner of the range sweep (BASELINE config 3), N=1 only ----------
     # The default configuration's search (r = 1) is HBM-bound; the metric also asks for the SAD
     # rate against the integer roofline, so the search kernel is timed alone at R=64, L=1 on

@@ -43,46 +43,58 @@ struct RsLv {        // one motion block at this level
 // NC candidate columns of one byte phase (4 bytes apart) x NDY candidate rows of a BxB anchor block.
 // `trow` = first window row of the chunk at the aligned word that holds the first column, `sh` = 8 *
 // (byte offset of that column inside the word).  Streams B + NDY - 1 window rows once.
-template <int B, int NC, int NDY>
+//
+// Written as a loop over groups of NDY anchor rows: the NDY shifted window rows an anchor row needs
+// rotate through NDY register slots, which is a static renaming when the loop advances NDY anchor rows
+// per trip.  The body is NDY x (one window row in, one anchor row in, NC x NDY x NW SADs): a few KB of
+// code that stays in the instruction cache (the straight-line version of a 16x16 item is ~30 KB and
+// measured 5 % slower: `no_instruction` stalls).
+template <int B, int NC, int NDY, int PA>  // PA: pitch of the anchor tile
 __device__ __forceinline__ void rs_item(const uint8_t* __restrict__ trow, const uint32_t sh,
                                         const uint8_t* __restrict__ ablk, uint32_t (&acc)[NC][NDY]) {
-  constexpr int NW = B >= 4 ? B / 4 : 1;      // words per block row
+  constexpr int NW = B >= 4 ? B / 4 : 1;
   constexpr uint32_t MASK = B >= 4 ? 0xffffffffu : (B == 2 ? 0xffffu : 0xffu);
-  constexpr int NS = NW + NC - 1;             // shifted words per row: column i uses s[i .. i+NW-1]
-  uint32_t a[B][NW];
+  constexpr int NS = NW + NC - 1;
+  uint32_t S[NDY][NS];
+  auto load_row = [&](const uint8_t* rowp, uint32_t (&dst)[NS]) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(rowp);
+    uint32_t raw[NS + 1];
 #pragma unroll
-  for (int k = 0; k < B; ++k) {
-    const uint8_t* q = ablk + k * 16;
-    if constexpr (B == 16) {
-      const uint4 v = *reinterpret_cast<const uint4*>(q);
-      a[k][0] = v.x; a[k][1] = v.y; a[k][2] = v.z; a[k][3] = v.w;
-    } else if constexpr (B == 8) {
-      const uint2 v = *reinterpret_cast<const uint2*>(q);
-      a[k][0] = v.x; a[k][1] = v.y;
-    } else if constexpr (B == 4) {
-      a[k][0] = *reinterpret_cast<const uint32_t*>(q);
-    } else if constexpr (B == 2) {
-      a[k][0] = *reinterpret_cast<const uint16_t*>(q);
-    } else {
-      a[k][0] = *q;
-    }
-  }
+    for (int k = 0; k <= NS; ++k) raw[k] = q[k];
 #pragma unroll
-  for (int t = 0; t < B + NDY - 1; ++t) {
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(trow + t * kRsPT);
-    uint32_t s[NS + 1];
+    for (int k = 0; k < NS; ++k) dst[k] = __funnelshift_r(raw[k], raw[k + 1], sh) & MASK;
+  };
 #pragma unroll
-    for (int k = 0; k <= NS; ++k) s[k] = q[k];
+  for (int d = 0; d < NDY - 1; ++d) load_row(trow + d * kRsPT, S[d]);
+#pragma unroll 1
+  for (int ar0 = 0; ar0 < B; ar0 += NDY) {
+    const uint8_t* tp = trow + (ar0 + NDY - 1) * kRsPT;
+    const uint8_t* ap = ablk + ar0 * PA;
 #pragma unroll
-    for (int k = 0; k < NS; ++k) s[k] = __funnelshift_r(s[k], s[k + 1], sh) & MASK;
+    for (int u = 0; u < NDY; ++u) {
+      if (ar0 + u < B) {  // uniform
+        load_row(tp + u * kRsPT, S[(u + NDY - 1) % NDY]);  // window row ar0 + u + NDY - 1
+        uint32_t a[NW];
+        const uint8_t* q = ap + u * PA;
+        if constexpr (B == 16) {
+          const uint4 v = *reinterpret_cast<const uint4*>(q);
+          a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+        } else if constexpr (B == 8) {
+          const uint2 v = *reinterpret_cast<const uint2*>(q);
+          a[0] = v.x; a[1] = v.y;
+        } else if constexpr (B == 4) {
+          a[0] = *reinterpret_cast<const uint32_t*>(q);
+        } else if constexpr (B == 2) {
+          a[0] = *reinterpret_cast<const uint16_t*>(q);
+        } else {
+          a[0] = *q;
+        }
 #pragma unroll
-    for (int dyi = 0; dyi < NDY; ++dyi) {
-      const int ar = t - dyi;
-      if (ar >= 0 && ar < B) {
+        for (int d = 0; d < NDY; ++d)
 #pragma unroll
-        for (int i = 0; i < NC; ++i)
+          for (int i = 0; i < NC; ++i)
 #pragma unroll
-          for (int k = 0; k < NW; ++k) acc[i][dyi] = sad4_acc(s[i + k], a[ar][k], acc[i][dyi]);
+            for (int k = 0; k < NW; ++k) acc[i][d] = sad4_acc(S[(u + d) % NDY][i + k], a[k], acc[i][d]);
       }
     }
   }
@@ -119,10 +131,13 @@ template <int B, int NDY, int NB>
 struct RsGeom {
   static constexpr int ROWS = B + 16 + NDY;                       // + slack rows a short last chunk streams
   static constexpr int WIN = (kRsPT * ROWS + 127) & ~127;
-  static constexpr int ANC = (16 * B + 127) & ~127;               // anchor box: 16 x B bytes
-  static constexpr int BLK = WIN + ANC;
+  static constexpr int BLK = WIN;                                 // one window per block
+  // the NB blocks of a CTA are horizontal neighbours: ONE anchor tile (one TMA request instead of NB)
+  static constexpr int PA = (NB * B) % 16 == 0 ? NB * B : ((NB * B + 15 + 15) & ~15);  // (+ 16-byte origin slack)
+  static constexpr int OFF_ANC = NB * BLK;
+  static constexpr int ANC = (PA * B + 127) & ~127;
   static constexpr int SADS = 17 * 17 * 2 + 2;                    // u16 per candidate (top level only)
-  static constexpr int OFF_SADS = NB * BLK;
+  static constexpr int OFF_SADS = OFF_ANC + ANC;
 };
 
 // B: block size at level `lvl`; TOP: exhaustive top level (EstimateMotionExhaustiveSearch semantics) or
@@ -130,19 +145,20 @@ struct RsGeom {
 // chunks per window, NB blocks per CTA; LAST: a full window has a 17th column (r = 8), searched by
 // 1-column items on an extra warp.
 template <int B, bool TOP, int NC, int NDY, int NCH, int NB, bool LAST, int MINB>
-__global__ void __launch_bounds__(NB * 4 * NCH + (LAST ? 32 : 0), MINB)
+__global__ void __launch_bounds__(NB * 4 * NCH + (LAST ? (NB * NCH + 31) / 32 * 32 : 0), MINB)
 hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ HbmaParams p, const int lvl) {
   using G = RsGeom<B, NDY, NB>;
   constexpr int MAIN = NB * 4 * NCH;
   static_assert(MAIN % 32 == 0, "main items must fill whole warps");
-  static_assert(!LAST || NB * NCH <= 32, "last-column items must fit one warp");
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ RsLv sLv[NB];
   __shared__ uint32_t sBest[NB], sViol[NB];
   const int tid = threadIdx.x;
-  const uint32_t per_frame = p.mvw * p.mvh;
-  const uint32_t n_blocks = per_frame * p.n_frames;  // < 2^31 (checked on the host)
+  // CTA -> NB horizontally adjacent motion blocks (frame f, block row by, blocks bx0 .. bx0 + NB - 1)
+  const uint32_t tiles_per_row = (p.mvw + NB - 1) / NB, tiles_per_frame = tiles_per_row * p.mvh;
+  const uint32_t f = blockIdx.x / tiles_per_frame, ti = blockIdx.x - f * tiles_per_frame;
+  const int by = (int)(ti / tiles_per_row), bx0 = (int)(ti - (uint32_t)by * tiles_per_row) * NB;
   const int r = (int)p.r;
   const int box_h = B + 2 * r;
   const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
@@ -157,12 +173,11 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
   uint32_t gb = 0;
   bool own = false;
   if (tid < NB) {
-    gb = blockIdx.x * NB + tid;
-    own = gb < n_blocks;
+    const int bx = bx0 + tid;
+    own = (uint32_t)bx < p.mvw;
+    gb = (f * p.mvh + (uint32_t)by) * p.mvw + (uint32_t)bx;
     RsLv v{};
     if (own) {
-      const uint32_t f = gb / per_frame, bi = gb - f * per_frame;
-      const int bx = (int)(bi % p.mvw), by = (int)(bi / p.mvw);
       if (!TOP) {
         const float2 m = p.mv[gb];  // integer valued (libs/motion.cpp:326-327, 403-404)
         cur = p.mad[gb];
@@ -181,21 +196,23 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
       v.x0 = x0; v.y0 = y0; v.ncx = ncx; v.ncy = ncy;
       v.csz = (ncy + NCH - 1) / NCH;
       v.sxb = x0 & 15;
-      v.aoff = ax & 15;
+      v.aoff = ((bx0 * B) & 15) + tid * B;  // inside the CTA's anchor tile
       sLv[tid] = v;
       sBest[tid] = 0xffffffffu;
       sViol[tid] = 0u;
+      // thread 0 (its block always exists) also fetches the anchor tile of the whole CTA
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
-                   "r"((uint32_t)(kRsPT * box_h + 16 * B)) : "memory");
+                   "r"((uint32_t)(kRsPT * box_h + (tid == 0 ? G::PA * B : 0))) : "memory");
       uint8_t* blk = smem + tid * G::BLK;
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
           ::"r"((uint32_t)__cvta_generic_to_shared(blk)), "l"(&maps.t), "r"(x0 & ~15), "r"(y0), "r"((int)f),
           "r"(bar_addr) : "memory");
-      asm volatile(
-          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          ::"r"((uint32_t)__cvta_generic_to_shared(blk + G::WIN)), "l"(&maps.a), "r"(ax & ~15), "r"(ay),
-          "r"((int)f + 1), "r"(bar_addr) : "memory");
+      if (tid == 0)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(smem + G::OFF_ANC)), "l"(&maps.a), "r"((bx0 * B) & ~15), "r"(ay),
+            "r"((int)f + 1), "r"(bar_addr) : "memory");
     } else {
       sLv[tid] = v;
       sBest[tid] = 0xffffffffu;
@@ -214,12 +231,14 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
     }
   }
   // ---- work items: static lane -> (block, byte phase, chunk) ----------------------------------
+  int it_j = -1, it_col0 = 0, it_dy0 = 0, it_nc = 0;  // this lane's item (the top level re-reads it below)
   if (tid < MAIN) {
     const int j = tid / (4 * NCH), rem = tid - j * (4 * NCH);
     const int ph = rem / NCH, c = rem - ph * NCH;
     const RsLv v = sLv[j];
     const int dy0 = c * v.csz;
     if (ph < v.ncx && dy0 < v.ncy) {
+      it_j = j; it_col0 = ph; it_dy0 = dy0; it_nc = NC;
       const uint8_t* blk = smem + j * G::BLK;
       const int sx = v.sxb + ph;
       uint32_t acc[NC][NDY];
@@ -227,7 +246,7 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
       for (int i = 0; i < NC; ++i)
 #pragma unroll
         for (int d = 0; d < NDY; ++d) acc[i][d] = 0;
-      rs_item<B, NC, NDY>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, blk + G::WIN + v.aoff, acc);
+      rs_item<B, NC, NDY, G::PA>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, smem + G::OFF_ANC + v.aoff, acc);
       rs_commit<NC, NDY, TOP>(acc, v, ph, dy0, &sBest[j],
                               reinterpret_cast<uint16_t*>(smem + G::OFF_SADS) + j * (G::SADS / 2));
     }
@@ -238,12 +257,13 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
       const RsLv v = sLv[j];
       const int dy0 = c * v.csz;
       if (v.ncx > 4 * NC && dy0 < v.ncy) {  // the window has a column 4*NC (= 16)
+        it_j = j; it_col0 = 4 * NC; it_dy0 = dy0; it_nc = 1;
         const uint8_t* blk = smem + j * G::BLK;
         const int sx = v.sxb + 4 * NC;
         uint32_t acc[1][NDY];
 #pragma unroll
         for (int d = 0; d < NDY; ++d) acc[0][d] = 0;
-        rs_item<B, 1, NDY>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, blk + G::WIN + v.aoff, acc);
+        rs_item<B, 1, NDY, G::PA>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, smem + G::OFF_ANC + v.aoff, acc);
         rs_commit<1, NDY, TOP>(acc, v, 4 * NC, dy0, &sBest[j],
                                reinterpret_cast<uint16_t*>(smem + G::OFF_SADS) + j * (G::SADS / 2));
       }
@@ -252,14 +272,22 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
   __syncthreads();
   if (TOP) {
     // "every candidate updated the minimum" <=> the SADs never increase along the scan order of the
-    // clamped window (libs/motion.cpp:312-337)
-    for (int e = tid; e < NB * 17 * 17; e += blockDim.x) {
-      const int j = e / (17 * 17), i = e - j * (17 * 17);
-      const int n = sLv[j].ncx * sLv[j].ncy;
-      if (i >= 1 && i < n) {
-        const uint16_t* s = reinterpret_cast<const uint16_t*>(smem + G::OFF_SADS) + j * (G::SADS / 2);
-        if (s[i] > s[i - 1]) sViol[j] = 1u;
+    // clamped window (libs/motion.cpp:312-337): every lane compares its candidates with their
+    // scan-order predecessors
+    if (it_j >= 0 && sViol[it_j] == 0u) {
+      const RsLv v = sLv[it_j];
+      const uint16_t* sd = reinterpret_cast<const uint16_t*>(smem + G::OFF_SADS) + it_j * (G::SADS / 2);
+      const int ndy = min(v.csz, v.ncy - it_dy0);
+      bool viol = false;
+      for (int i = 0; i < it_nc; ++i) {
+        const int col = it_col0 + 4 * i;
+        if (col < v.ncx)
+          for (int d = 0; d < ndy; ++d) {
+            const int idx = (it_dy0 + d) * v.ncx + col;
+            if (idx > 0 && sd[idx] > sd[idx - 1]) viol = true;
+          }
       }
+      if (viol) sViol[it_j] = 1u;
     }
     __syncthreads();
   }
@@ -290,27 +318,31 @@ template <int B, bool TOP, int NC, int NDY, int NCH, int NB, bool LAST, int MINB
 cudaError_t launch_rs(const HbmaParams& p, uint32_t lvl, cudaStream_t st) {
   using G = RsGeom<B, NDY, NB>;
   constexpr int SMEM = G::OFF_SADS + (TOP ? NB * G::SADS : 0);
-  constexpr int THREADS = NB * 4 * NCH + (LAST ? 32 : 0);
+  constexpr int THREADS = NB * 4 * NCH + (LAST ? (NB * NCH + 31) / 32 * 32 : 0);
   EbmaMaps maps;
   const uint32_t n_slots = p.n_frames + 1;
   const uint8_t* base = p.pyr + p.lay.off[lvl];
   if (!encode_box(&maps.t, base, p.lay.w[lvl], p.lay.h[lvl], p.lay.pitch[lvl], p.lay.slot_bytes, n_slots, kRsPT,
                   B + 2 * p.r) ||
-      !encode_box(&maps.a, base, p.lay.w[lvl], p.lay.h[lvl], p.lay.pitch[lvl], p.lay.slot_bytes, n_slots, 16, B))
+      !encode_box(&maps.a, base, p.lay.w[lvl], p.lay.h[lvl], p.lay.pitch[lvl], p.lay.slot_bytes, n_slots, G::PA, B))
     return cudaErrorNotSupported;
+  static_assert(G::PA <= 256, "TMA box limit");
   auto kern = hbma_rs_kernel<B, TOP, NC, NDY, NCH, NB, LAST, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   if (e != cudaSuccess) return e;
-  const uint64_t n_blocks = (uint64_t)p.mvw * p.mvh * p.n_frames;
-  kern<<<(uint32_t)((n_blocks + NB - 1) / NB), THREADS, SMEM, st>>>(maps, p, (int)lvl);
+  const uint64_t n_ctas = (uint64_t)((p.mvw + NB - 1) / NB) * p.mvh * p.n_frames;
+  kern<<<(uint32_t)n_ctas, THREADS, SMEM, st>>>(maps, p, (int)lvl);
   return cudaGetLastError();
 }
 
-// range classes: r = 5..8 -> windows up to 17 x 17: 4 columns x 6 rows per item, 3 chunks, 8 blocks per CTA
-// and the 17th column on a fifth warp...; r = 3, 4 -> up to 9 x 9: 3 columns x 5 rows, 2 chunks, 16 blocks.
+// range classes: r = 5..8 -> windows up to 17 x 17: 4 columns x 6 rows per item, 3 chunks, 8 blocks per
+// CTA and the 17th column on a fourth warp; r = 3, 4 -> up to 9 x 9: 3 columns x 5 rows, 2 chunks, 16
+// blocks.  (More blocks per CTA for the small levels measured SLOWER -- 16 / 32 blocks at 8x8 / 4x4:
+// 263 / 186 us against 206 / 114 us for 45 pairs of 1080p: those levels are bound by the two TMA
+// requests every block issues, not by a CTA's fixed latency.)
 template <int B, bool TOP>
 cudaError_t launch_rs_class(const HbmaParams& p, uint32_t lvl, cudaStream_t st) {
-  constexpr int MINB = B == 16 ? 4 : 6;
+  constexpr int MINB = B == 16 ? 5 : 6;
   if (p.r >= 5) return launch_rs<B, TOP, 4, 6, 3, 8, true, MINB>(p, lvl, st);
   return launch_rs<B, TOP, 3, 5, 2, 16, false, MINB>(p, lvl, st);
 }
