@@ -262,6 +262,12 @@ int svc_decode_frames_device(int device, void* cuda_stream, const uint8_t* d_rec
                              uint32_t tbw, uint32_t tbh, uint32_t fg_quant_step,
                              uint32_t bg_quant_step, const svc_rect* gaze, float* d_out_bgr);
 
+/* Self-test of the decoder's dequantiser (round(c / q) * q, libs/decoder.cpp:137-144): the kernels
+ * replace the IEEE division by a reciprocal + two fused multiply-adds for steps <= 4096 and
+ * |c| <= 2^18.  Compares that quotient with the IEEE division for EVERY float of that range (both
+ * signs) and every step in [q_lo, q_hi]; *mismatches must come back 0. */
+int svc_selftest_dequant(int device, uint32_t q_lo, uint32_t q_hi, uint64_t* mismatches);
+
 /* Stream validator: record geometry implied by a 32-byte header on the encoder side
  * (SerializeEncodedFrame iterates the UNPADDED frame, libs/encoder.cpp:243-244) and on
  * the decoder side (Decoder::operator() iterates the PADDED frame, libs/decoder.cpp:

@@ -112,5 +112,7 @@ struct DecodeParams {
   float* out;                    // n_frames x ph x pw x 3 interleaved BGR (16-byte aligned)
 };
 cudaError_t launch_decode(const DecodeParams& p, cudaStream_t st);
+// exhaustive check of the decoder's division-free quotient against __fdiv_rn (see k_idct.cu)
+cudaError_t run_dequant_selftest(uint32_t q_lo, uint32_t q_hi, unsigned long long* d_mismatches, cudaStream_t st);
 
 }  // namespace svc

@@ -19,9 +19,18 @@
 //     phase and no barrier; the 17th column of a full window forms its own 1-column items;
 //   * a window is 48 x (B + 2r) bytes (1.6 KB for the 16x16 level instead of 9.9 KB with copies), so
 //     8 blocks per 128-thread CTA need 15 KB and the register file, not shared memory, limits the
-//     CTAs per SM (4 CTAs: while one waits for its windows three others keep the ALU pipe busy);
+//     CTAs per SM (5-6 CTAs: while one waits for its windows the others keep the ALU pipe busy);
 //   * items map to lanes statically (block = lane / 12 ..): no pooled item decode;
-//   * the anchor block lives in registers (B*B/4), each item keeps 4 x 6 running SADs.
+//   * the 8 blocks of a CTA are horizontal neighbours and share ONE anchor tile (one TMA request);
+//     an item keeps 4 x 6 running SADs and reads each anchor row once, when the row loop reaches it.
+// Measured and rejected on the way (45 pairs of 1080p, R=64/L=4, us per level 16x16 / 8x8 / 4x4):
+//   straight-line items 589 / 201 / 119 (this file: 555 / 206 / 113); 9 rows per item, 12 blocks per
+//   CTA: 128 registers, 4 CTAs per SM, -13 %; a two-stage TMA pipeline over consecutive block groups
+//   inside a persistent CTA: -20 %; warps uniform in the chunk index (a 5-row instance for the short
+//   chunk): the 8 windows a warp then reads lie 128-byte aligned in shared memory -> bank conflicts, -20 %;
+//   16 / 32 blocks per CTA for the small levels: 263 / 186; windows staged by 16-byte global loads
+//   instead of TMA: 613 / 248 / 140.  ncu of the final 16x16 level: ALU pipe 85 % busy, 64 % of all
+//   instructions are VABSDIFF4, 7 % SHF (profiles/r02_ncu_hbma_rs_*.txt).
 #include <float.h>
 
 #include "common.cuh"

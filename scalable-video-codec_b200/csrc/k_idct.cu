@@ -20,6 +20,107 @@
 
 namespace svc {
 
+// ---- dequantiser: round(c / q) * q, libs/decoder.cpp:140-142 ----------------------------------------
+// The reference divides a float coefficient by the (integer) step in IEEE single precision, rounds half
+// away from zero and multiplies back.  __fdiv_rn is a ~15-instruction subroutine per coefficient, as
+// expensive as the inverse transform itself.  For steps up to 4096 and |c| <= 2^18 (a 16x16 block of
+// 255s has a DC coefficient of 4080) the correctly rounded quotient is instead obtained with Markstein's
+// sequence from the correctly rounded reciprocal rq = RN(1/q):
+//     y = RN(c * rq);  e = RN(c - q * y) (one FMA);  d = RN(y + e * rq) (one FMA)
+// svc_selftest_dequant() compares it with __fdiv_rn for EVERY float in [0, 2^18] and every step of a
+// range (tests/test_decode.py runs q = 1 .. 4096: zero mismatches); anything outside that domain --
+// larger steps, huge / non-finite coefficients of a corrupt stream -- takes the IEEE division.
+constexpr float kDequantFastMaxAbs = 262144.0f;
+constexpr uint32_t kDequantFastMaxStep = 4096u;
+
+struct QuantStep {
+  float q, rq;
+  bool fast;
+};
+
+__device__ __forceinline__ QuantStep make_quant_step(const uint32_t step) {
+  QuantStep s;
+  s.q = (float)step;
+  s.rq = __frcp_rn(s.q);
+  s.fast = step <= kDequantFastMaxStep;
+  return s;
+}
+
+__device__ __forceinline__ float quotient_rn(const float c, const QuantStep& s) {
+  if (s.fast && fabsf(c) <= kDequantFastMaxAbs) {
+    const float y = __fmul_rn(c, s.rq);
+    const float e = __fmaf_rn(-s.q, y, c);
+    return __fmaf_rn(e, s.rq, y);
+  }
+  return __fdiv_rn(c, s.q);
+}
+
+// round(c / q) * q.  The FMA sequence may differ from the division where the quotient underflows
+// (|c / q| < 2^-126: double rounding in the subnormal range, and -0 comes out as +0); every such quotient
+// rounds to zero, so only the sign of that zero needs restoring: the result always has the sign of c.
+__device__ __forceinline__ float dequant_value(const float c, const QuantStep& s) {
+  return copysignf(__fmul_rn(roundf(quotient_rn(c, s)), s.q), c);
+}
+
+__device__ __forceinline__ float dequant(const uint32_t w, const QuantStep& s) {
+  return dequant_value(__uint_as_float(w), s);
+}
+
+// N coefficients at once: ONE (almost never taken) branch for the whole group instead of a
+// divergence region per coefficient -- the straight path is 3 FMA-pipe instructions + the rounding.
+template <int N>
+__device__ __forceinline__ void dequant_group(const uint32_t (&w)[N], const QuantStep& s, float (&out)[N]) {
+  // |c| <= 2^18 for the whole group <=> the largest magnitude bit pattern is at most that of 2^18
+  // (infinities and NaNs have larger patterns than any finite float)
+  uint32_t big = 0u;
+#pragma unroll
+  for (int i = 0; i < N; ++i) big = max(big, w[i] & 0x7fffffffu);
+  const bool all_finite_small = s.fast && big <= 0x48800000u;
+  if (all_finite_small) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float c = __uint_as_float(w[i]);
+      const float y = __fmul_rn(c, s.rq);
+      const float e = __fmaf_rn(-s.q, y, c);
+      out[i] = copysignf(__fmul_rn(roundf(__fmaf_rn(e, s.rq, y)), s.q), c);
+    }
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) out[i] = dequant(w[i], s);
+  }
+}
+
+// every float bit pattern in [-2^18, 2^18] x every step in [q_lo, q_hi]: dequantised value with the fast
+// quotient vs with the IEEE division, bit for bit; mismatches[1] keeps one offending (c, step) pair
+__global__ void __launch_bounds__(256) dequant_selftest_kernel(const uint32_t q_lo, const uint32_t q_hi,
+                                                               unsigned long long* mismatches) {
+  constexpr uint32_t kMaxBits = 0x48800000u;  // 2^18
+  unsigned long long bad = 0;
+  for (uint32_t step = q_lo + blockIdx.y; step <= q_hi; step += gridDim.y) {
+    const QuantStep s = make_quant_step(step);
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= kMaxBits; b += (uint64_t)gridDim.x * blockDim.x) {
+      const float c = __uint_as_float((uint32_t)b);
+      const float ref = __fmul_rn(roundf(__fdiv_rn(c, s.q)), s.q);  // libs/decoder.cpp:140-142
+      const float got = dequant_value(c, s);
+      const float refn = __fmul_rn(roundf(__fdiv_rn(-c, s.q)), s.q);
+      const float gotn = dequant_value(-c, s);
+      const bool m = (__float_as_uint(ref) != __float_as_uint(got)) || (__float_as_uint(refn) != __float_as_uint(gotn));
+      if (m) {
+        ++bad;
+        mismatches[1] = ((unsigned long long)step << 32) | (uint32_t)b;
+      }
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t run_dequant_selftest(uint32_t q_lo, uint32_t q_hi, unsigned long long* d_mismatches, cudaStream_t st) {
+  const uint32_t ny = q_hi - q_lo + 1u < 64u ? q_hi - q_lo + 1u : 64u;
+  dequant_selftest_kernel<<<dim3(kNumSms * 8, ny), 256, 0, st>>>(q_lo, q_hi, d_mismatches);
+  return cudaGetLastError();
+}
+
+
 #define SVC_C4 0.35355339059327376220f
 #define SVC_A  0.49039264020161522456f
 #define SVC_B2 0.46193976625564337806f
@@ -128,6 +229,9 @@ idct8x8_decode_kernel(const DecodeParams p) {
     const uint32_t x0 = (bx0 + lane) * 8u, y0 = by * 8u;
     const bool gazed = p.has_gaze && x0 >= p.gaze_x && x0 < p.gaze_x + p.gaze_w && y0 >= p.gaze_y &&
                        y0 < p.gaze_y + p.gaze_h;
+    // (this kernel keeps the IEEE division: with 64 coefficients per lane in registers the division-free
+    // forms measured slower here -- 4K microbench 84 % of the copy peak with __fdiv_rn, 78-83 % with the
+    // per-coefficient fast quotient, 68 % with the grouped one; the 4x4 and 16x16 kernels gain from it)
     const float q = (float)(gazed ? 1u : (type == 0u ? p.bg_q : p.fg_q));
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -173,10 +277,6 @@ __device__ __forceinline__ void idct4(float& x0, float& x1, float& x2, float& x3
   const float o0 = fmaf(a, x1, b * x3), o1 = fmaf(b, x1, -a * x3);
   x0 = p + o0; x3 = p - o0;
   x1 = q + o1; x2 = q - o1;
-}
-
-__device__ __forceinline__ float dequant(const uint32_t w, const float q) {
-  return __fmul_rn(roundf(__fdiv_rn(__uint_as_float(w), q)), q);  // libs/decoder.cpp:140-142
 }
 
 __device__ __forceinline__ bool in_gaze(const DecodeParams& p, const uint32_t x0, const uint32_t y0) {
@@ -244,7 +344,7 @@ idct4x4_decode_kernel(const DecodeParams p) {
   const bool active = t < n_act;
   if (active) {
     const uint32_t* rec = stage + t * kRecW4;  // 49 lane + const: conflict free
-    const float q = (float)(in_gaze(p, (bx0 + t) * 4u, by * 4u) ? 1u : (rec[0] == 0u ? p.bg_q : p.fg_q));
+    const QuantStep q = make_quant_step(in_gaze(p, (bx0 + t) * 4u, by * 4u) ? 1u : (rec[0] == 0u ? p.bg_q : p.fg_q));
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
 #pragma unroll
@@ -342,14 +442,16 @@ idct16x16_decode_kernel(const DecodeParams p) {
   const bool active = b < n_act;
   const uint32_t* rec = stage + (b & 3u) * kRecW16 + (b >> 2) * kStageHalfD16;
   float* buf = tmp + b * kTmpBlkD16;
-  const float q = !active ? 1.f : (float)(in_gaze(p, (bx0 + b) * 16u, by * 16u) ? 1u : (rec[0] == 0u ? p.bg_q : p.fg_q));
+  const QuantStep q = make_quant_step(!active ? 1u : (in_gaze(p, (bx0 + b) * 16u, by * 16u) ? 1u : (rec[0] == 0u ? p.bg_q : p.fg_q)));
   float px[48];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     {
       float X[16], x[16];
+      uint32_t w[16];
 #pragma unroll
-      for (int ky = 0; ky < 16; ++ky) X[ky] = active ? dequant(rec[1 + c * 256 + ky * 16 + r], q) : 0.f;
+      for (int ky = 0; ky < 16; ++ky) w[ky] = active ? rec[1 + c * 256 + ky * 16 + r] : 0u;
+      dequant_group<16>(w, q, X);
       idct16(X, x);
 #pragma unroll
       for (int y = 0; y < 16; ++y) buf[y * kTmpPitchD16 + r] = x[y];

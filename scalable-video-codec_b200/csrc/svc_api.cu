@@ -531,6 +531,30 @@ int svc_decode_frame_blocks(const uint8_t* frame_records, uint32_t padded_w, uin
   return SVC_OK;
 }
 
+int svc_selftest_dequant(int device, uint32_t q_lo, uint32_t q_hi, uint64_t* mismatches) {
+  if (!mismatches || q_lo == 0 || q_hi < q_lo) return fail(SVC_ERR_INVALID_ARG, "bad arguments");
+  int rc = prepare_device(device);
+  if (rc) return rc;
+  cudaStream_t st = nullptr;
+  rc = thread_stream(device, &st);
+  if (rc) return rc;
+  DevBuf cnt;
+  CU(cnt.alloc(2 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(unsigned long long), st));
+  CU(run_dequant_selftest(q_lo, q_hi, cnt.as<unsigned long long>(), st));
+  unsigned long long h[2] = {0, 0};
+  CU(cudaMemcpyAsync(h, cnt.p, sizeof h, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *mismatches = h[0];
+  if (h[0]) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "dequantiser self-test: %llu mismatches, e.g. step %u, coefficient bits 0x%08x",
+             h[0], (unsigned)(h[1] >> 32), (unsigned)(h[1] & 0xffffffffu));
+    g_err = msg;
+  }
+  return SVC_OK;
+}
+
 // ---- memory helpers -------------------------------------------------------------
 
 void* svc_host_alloc(size_t bytes) {

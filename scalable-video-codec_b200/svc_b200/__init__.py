@@ -8,7 +8,7 @@ frame-range sharding logic.  There is no CPU implementation here: importing
 works without a GPU, every compute call raises SvcError without one.
 """
 from .binding import (  # noqa: F401
-    SvcError, lib, lib_path, device_count, sad_peak, padded_dim, serialized_frame_bytes,
+    SvcError, lib, lib_path, device_count, sad_peak, selftest_dequant, padded_dim, serialized_frame_bytes,
     write_header, EstimateMotionHierarchical, EstimateMotionHierarchical16x16Sse2,
     EstimateMotionExhaustiveSearch, y_pyramid, dct_planar, encode_frame_stream,
     patch_block_types, stream_layout, gaze_rect, decode_frame_blocks, decode_frames_device, Session, SessionConfig, PinnedBuffer, DeviceBuffer,

@@ -126,6 +126,16 @@ def sad_peak(device: int = 0) -> float:
     return v.value
 
 
+def selftest_dequant(q_lo: int, q_hi: int, device: int = 0) -> int:
+    """Mismatches between the decoder's division-free quotient and the IEEE division over every float
+    in [-2^18, 2^18] and every quantisation step in [q_lo, q_hi] (must be 0)."""
+    n = C.c_uint64(0)
+    _check(lib().svc_selftest_dequant(C.c_int(device), C.c_uint32(q_lo), C.c_uint32(q_hi), C.byref(n)))
+    if n.value:
+        print(lib().svc_last_error().decode())
+    return n.value
+
+
 def padded_dim(a: int, mv_block: int, levels: int) -> int:
     return int(lib().svc_padded_dim(a, mv_block, levels))
 

@@ -154,3 +154,12 @@ def test_gpu_encode_decode_round_trip_square_blocks(gpu, tb):
     dec = gpu.decode_frame_blocks(st, w, h, fg_quant_step=1, bg_quant_step=1, tbw=tb, tbh=tb)
     err = np.abs(dec - f[1].astype(np.float32))
     assert err.max() <= 0.5 * tb + 0.5 and err.mean() < 0.4
+
+
+@pytest.mark.gpu
+def test_dequantiser_quotient_is_the_ieee_division_exhaustively(gpu):
+    """The decoder kernels compute round(c / q) * q (libs/decoder.cpp:137-144) without the IEEE
+    division subroutine (reciprocal + two FMAs, k_idct.cu).  That quotient must be bit-identical
+    to the division for every float c in [-2^18, 2^18] and every step the fast path accepts."""
+    assert gpu.selftest_dequant(1, 4096) == 0
+    assert gpu.selftest_dequant(4097, 4100) == 0  # beyond the fast-path limit: the IEEE division itself
