@@ -554,9 +554,12 @@ def run_ours(a):
                "ms_per_step": ms_e2e, "steps": n_e2e,
                "api": "svc_session_encode (pinned host buffers; H2D | kernels | D2H pipelined)"}
         if not a.no_parity:
-            par_out["e2e_host_buffers"] = (h_mv.view(np.float32, (n_enc, sess.mv_field_h, sess.mv_field_w, 2)),
-                                           h_mad.view(np.float32, (n_enc, sess.mv_field_h, sess.mv_field_w)),
-                                           h_st.view(np.uint8, (n_enc, fst)).__getitem__)
+            # (copies of the sampled frames' records: the copy-only probe below reuses the landing zone)
+            st_view = h_st.view(np.uint8, (n_enc, fst))
+            st_host = {k: st_view[k].copy() for k in picks_}
+            par_out["e2e_host_buffers"] = (h_mv.view(np.float32, (n_enc, sess.mv_field_h, sess.mv_field_w, 2)).copy(),
+                                           h_mad.view(np.float32, (n_enc, sess.mv_field_h, sess.mv_field_w)).copy(),
+                                           st_host.__getitem__)
     # ---------------- copy-only ceiling of the e2e figure, measured in this run ----------------------
     # The same pinned buffers and byte volumes moved by plain cudaMemcpyAsync on two streams, no kernels
     # (tools/pcie_probe.py, mode `both`), all ranks at once: what the host <-> device path of this box
