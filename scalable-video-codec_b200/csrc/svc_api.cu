@@ -620,11 +620,14 @@ struct svc_session {
   float* d_scratch = nullptr;  // generic DCT path only
   uint32_t scratch_frames = 0;
   // host path staging (double buffered), allocated on first use
-  uint8_t* d_in[2] = {nullptr, nullptr};
+  static constexpr int kInRing = 8;  // input staging slots: the upload runs up to 8 chunks ahead of the kernels
+  uint8_t* d_in[kInRing] = {};
+  cudaEvent_t ev_in_ring[kInRing] = {}, ev_used[kInRing] = {};
+  uint32_t in_ring = 2;
   float* d_mv[2] = {nullptr, nullptr};
   float* d_mad[2] = {nullptr, nullptr};
   uint8_t* d_st[2] = {nullptr, nullptr};
-  uint32_t* d_bt[2] = {nullptr, nullptr};
+  uint32_t* d_bt[8] = {};  // (one per input slot)
   cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
   bool staging = false;
   uint32_t host_chunk = 16;  // frames per pipeline stage of svc_session_encode
@@ -755,15 +758,21 @@ int fork_motion(svc_session* s) {
 }
 
 void free_staging(svc_session* s) {
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < svc_session::kInRing; ++b) {
     cudaFree(s->d_in[b]);
+    cudaFree(s->d_bt[b]);
+    s->d_in[b] = nullptr;
+    s->d_bt[b] = nullptr;
+    if (s->ev_in_ring[b]) cudaEventDestroy(s->ev_in_ring[b]);
+    if (s->ev_used[b]) cudaEventDestroy(s->ev_used[b]);
+    s->ev_in_ring[b] = s->ev_used[b] = nullptr;
+  }
+  for (int b = 0; b < 2; ++b) {
     cudaFree(s->d_mv[b]);
     cudaFree(s->d_mad[b]);
     cudaFree(s->d_st[b]);
-    cudaFree(s->d_bt[b]);
-    s->d_in[b] = s->d_st[b] = nullptr;
+    s->d_st[b] = nullptr;
     s->d_mv[b] = s->d_mad[b] = nullptr;
-    s->d_bt[b] = nullptr;
     if (s->ev_in[b]) cudaEventDestroy(s->ev_in[b]);
     if (s->ev_comp[b]) cudaEventDestroy(s->ev_comp[b]);
     if (s->ev_out[b]) cudaEventDestroy(s->ev_out[b]);
@@ -780,12 +789,19 @@ int alloc_staging(svc_session* s) {
   const size_t mvn = (size_t)s->info.mv_field_w * s->info.mv_field_h;
   CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
-  for (int b = 0; b < 2; ++b) {
+  // input ring: as many slots as fit 4 GB (at least 2): inputs are a fifth of the traffic, and an upload
+  // that runs ahead keeps host-memory reads out of the way of the record writes that bound the path
+  s->in_ring = (uint32_t)std::max<size_t>(2, std::min<size_t>(svc_session::kInRing, (4ull << 30) / std::max<size_t>(1, B * s->info.frame_in_bytes)));
+  for (uint32_t b = 0; b < s->in_ring; ++b) {
     CU(cudaMalloc(&s->d_in[b], B * s->info.frame_in_bytes));
+    CU(cudaMalloc(&s->d_bt[b], B * mvn * sizeof(uint32_t)));
+    CU(cudaEventCreateWithFlags(&s->ev_in_ring[b], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s->ev_used[b], cudaEventDisableTiming));
+  }
+  for (int b = 0; b < 2; ++b) {
     CU(cudaMalloc(&s->d_mv[b], B * mvn * sizeof(float2)));
     CU(cudaMalloc(&s->d_mad[b], B * mvn * sizeof(float)));
     CU(cudaMalloc(&s->d_st[b], B * s->info.frame_stream_bytes));
-    CU(cudaMalloc(&s->d_bt[b], B * mvn * sizeof(uint32_t)));
     CU(cudaEventCreateWithFlags(&s->ev_in[b], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s->ev_comp[b], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s->ev_out[b], cudaEventDisableTiming));
@@ -1039,29 +1055,31 @@ int svc_session_encode(svc_session* s, const uint8_t* frames, uint32_t n_frames,
   const size_t mvn = (size_t)s->info.mv_field_w * s->info.mv_field_h;
   const size_t fin = s->info.frame_in_bytes, fst = s->info.frame_stream_bytes;
   uint32_t done_in = 0, done_enc = 0, chunk = 0;
-  // 3-stage pipeline over batches: H2D (s_in) | kernels (stream) | D2H (s_out)
+  // 3-stage pipeline over chunks: H2D (s_in) | kernels (stream) | D2H (s_out).  Outputs are double
+  // buffered (slot b); inputs go through a ring of in_ring slots (slot bi), so the upload -- a fifth of
+  // the traffic -- runs well ahead of the kernels instead of in lock step with the record download.
   while (done_in < n_frames) {
     const int b = chunk & 1;
+    const uint32_t bi = chunk % s->in_ring;
     // PCIe-bound: small chunks keep H2D | kernels | D2H overlapped and the exposed head
     // and tail of the pipeline short
     const uint32_t m = std::min(std::min(s->info.max_batch, s->host_chunk), n_frames - done_in);
     const uint32_t ne = s->have_prev ? m : m - 1;
-    if (chunk >= 2) {
-      CU(cudaStreamWaitEvent(s->s_in, s->ev_comp[b], 0));   // d_in[b] consumed
-      CU(cudaStreamWaitEvent(s->stream, s->ev_out[b], 0));  // outputs[b] drained
-    }
-    CU(cudaMemcpyAsync(s->d_in[b], frames + (size_t)done_in * fin, (size_t)m * fin,
+    if (chunk >= s->in_ring) CU(cudaStreamWaitEvent(s->s_in, s->ev_used[bi], 0));  // d_in[bi] consumed
+    if (chunk >= 2) CU(cudaStreamWaitEvent(s->stream, s->ev_out[b], 0));           // outputs[b] drained
+    CU(cudaMemcpyAsync(s->d_in[bi], frames + (size_t)done_in * fin, (size_t)m * fin,
                        cudaMemcpyHostToDevice, s->s_in));
     if (block_types && ne)
-      CU(cudaMemcpyAsync(s->d_bt[b], block_types + done_enc * mvn, ne * mvn * sizeof(uint32_t),
+      CU(cudaMemcpyAsync(s->d_bt[bi], block_types + done_enc * mvn, ne * mvn * sizeof(uint32_t),
                          cudaMemcpyHostToDevice, s->s_in));
-    CU(cudaEventRecord(s->ev_in[b], s->s_in));
-    CU(cudaStreamWaitEvent(s->stream, s->ev_in[b], 0));
+    CU(cudaEventRecord(s->ev_in_ring[bi], s->s_in));
+    CU(cudaStreamWaitEvent(s->stream, s->ev_in_ring[bi], 0));
     uint32_t ne2 = 0;
-    rc = encode_batch_device(s, s->d_in[b], m, (mv || mad) ? s->d_mv[b] : nullptr,
+    rc = encode_batch_device(s, s->d_in[bi], m, (mv || mad) ? s->d_mv[b] : nullptr,
                              mad ? s->d_mad[b] : nullptr, stream ? s->d_st[b] : nullptr,
-                             block_types ? s->d_bt[b] : nullptr, &ne2);
+                             block_types ? s->d_bt[bi] : nullptr, &ne2);
     if (rc) return rc;
+    CU(cudaEventRecord(s->ev_used[bi], s->stream));  // (K3 is the only reader of the frames and block types)
     CU(cudaEventRecord(s->ev_comp[b], s->stream));
     CU(cudaStreamWaitEvent(s->s_out, s->ev_comp[b], 0));
     rc = join_motion(s, s->s_out);  // motion vectors come from the motion stream
