@@ -404,7 +404,7 @@ def run_ours(a):
     seq.frames(in_lo, in_hi, out=frames)
 
     d_in = torch.empty(F * fin, dtype=torch.uint8, device="cuda")
-    d_st = torch.empty(n_enc * fst, dtype=torch.uint8, device="cuda")
+    d_st = torch.empty(F * fst, dtype=torch.uint8, device="cuda")  # (F, not n_enc: the stage timings run whole batches)
     d_mv = torch.empty(n_enc * mvn * 2, dtype=torch.float32, device="cuda")
     d_mad = torch.empty(n_enc * mvn, dtype=torch.float32, device="cuda")
     svc.binding._check(svc.lib().svc_memcpy_h2d(local, d_in.data_ptr(), h_in.ptr, F * fin))

@@ -307,7 +307,7 @@ constexpr int kF1Groups = (kF1W + 3) / 4;                     // 13 groups of 4 
 constexpr int kF1Rpt = 4, kF1Strips = (kF1H + kF1Rpt - 1) / kF1Rpt;  // 9 strips of 4 rows
 constexpr int kF0BoxW = 144, kF0BoxH = 2 * kF1H + 3;          // 144 x 73: TMA box of level l
 constexpr int kF0Rows = 2 * kF1Rpt * kF1Strips + 3;           // 75: rows the phase-1 threads may touch
-constexpr int kF1Pitch = 64;                                   // level l+1 region: column j at byte j + 2
+constexpr int kF1Pitch = 80, kF1Off = 14;                      // level l+1 region: column j at byte j + 14 (core at byte 16)
 constexpr int kF2Rpt = 2;                                      // phase 2: level l+2 rows per thread
 constexpr int kFusedThreads = 128;
 static_assert((kF2TileW / 4) * (kF2TileH / kF2Rpt) <= kFusedThreads, "phase 2 does not fit the CTA");
@@ -384,20 +384,22 @@ pyr_down2_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restric
 #pragma unroll
     for (int y = 0; y < kF1Rpt; ++y) {
       const int i1 = kF1Rpt * sidx + y;  // region row
-      // shared copy (column j at byte j + 2: the group sits at byte 4g + 2, 2-byte aligned)
-      uint16_t* q = reinterpret_cast<uint16_t*>(t1 + i1 * kF1Pitch + 4 * g + 2);
+      // shared copy (the group sits at byte 4g + 14, 2-byte aligned)
+      uint16_t* q = reinterpret_cast<uint16_t*>(t1 + i1 * kF1Pitch + 4 * g + kF1Off);
       q[0] = (uint16_t)px[y];
       q[1] = (uint16_t)(px[y] >> 16);
-      // core of the region -> global memory (u = 2x0 .. 2x0+47, v = 2y0 .. 2y0+15)
-      const int v = v0 + i1, u = u0 + 4 * g;
-      if (i1 >= 2 && i1 < 2 + 2 * kF2TileH && v < (int)h1) {
-        uint8_t* drow = slot + off1 + (uint64_t)v * pitch1;
-        if (g >= 1 && u < (int)w1) *reinterpret_cast<uint16_t*>(drow + u) = (uint16_t)px[y];
-        if (g < kF1Groups - 1 && u + 2 < (int)w1) *reinterpret_cast<uint16_t*>(drow + u + 2) = (uint16_t)(px[y] >> 16);
-      }
     }
   }
   __syncthreads();
+  // core of the region (u = 2x0 .. 2x0+47, v = 2y0 .. 2y0+31) -> global memory: three 16-byte stores per
+  // row (the core starts at byte 16 of a region row and at a multiple of 48 in the level)
+  for (int e = threadIdx.x; e < 2 * kF2TileH * 3; e += kFusedThreads) {
+    const int row = e / 3, ch = e - row * 3;
+    const int v = 2 * y0 + row, u = 2 * x0 + 16 * ch;
+    if (v < (int)h1 && u < (int)w1)
+      *reinterpret_cast<uint4*>(slot + off1 + (uint64_t)v * pitch1 + u) =
+          *reinterpret_cast<const uint4*>(t1 + (row + 2) * kF1Pitch + 16 + 16 * ch);
+  }
   // ---- level l+1: BORDER_REFLECT_101 of the region's out-of-image part ---------------------------
   {
     const int xe = min(x0 + kF2TileW, (int)w2), ye = min(y0 + kF2TileH, (int)h2);
@@ -417,7 +419,7 @@ pyr_down2_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restric
     }
     if (cu_lo < 0 || cu_hi >= (int)w1) {  // CTA-uniform
       for (int rr = threadIdx.x; rr <= rv_hi - rv_lo; rr += kFusedThreads) {
-        uint8_t* trow = t1 + (rv_lo + rr - v0) * kF1Pitch + 2 - u0;  // trow[k] = level l+1 column k
+        uint8_t* trow = t1 + (rv_lo + rr - v0) * kF1Pitch + kF1Off - u0;  // trow[k] = level l+1 column k
         for (int k = cu_lo; k < 0; ++k) trow[k] = trow[reflect101_near(k, (int)w1)];
         for (int k = max((int)w1, cu_lo); k <= cu_hi; ++k) trow[k] = trow[reflect101_near(k, (int)w1)];
       }
@@ -429,9 +431,9 @@ pyr_down2_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restric
     const int g = threadIdx.x % (kF2TileW / 4), sidx = threadIdx.x / (kF2TileW / 4);
     const int ox = x0 + 4 * g, oy = y0 + kF2Rpt * sidx;
     if (ox < (int)w2 && oy < (int)h2) {
-      // output q = 4g + i reads region columns 2q .. 2q + 4 = bytes 2q + 2 .. = (8g - 4) + 6 + 2i ..
+      // output q = 4g + i reads region columns 2q .. 2q + 4 = bytes 2q + 14 .. = (8g + 8) + 6 + 2i ..
       uint32_t px[kF2Rpt];
-      pyr_down_rows<kF2Rpt, kF1Pitch, false>(t1 + (2 * kF2Rpt * sidx) * kF1Pitch + 8 * g - 4, px);
+      pyr_down_rows<kF2Rpt, kF1Pitch, true>(t1 + (2 * kF2Rpt * sidx) * kF1Pitch + 8 * g + 8, px);
 #pragma unroll
       for (int y = 0; y < kF2Rpt; ++y)
         if (oy + y < (int)h2) *reinterpret_cast<uint32_t*>(slot + off2 + (uint64_t)(oy + y) * pitch2 + ox) = px[y];

@@ -116,6 +116,39 @@ def test_ransac_matches_the_compiled_reference(seg, oracle, seed, params):
         assert np.float32(rmse) == np.float32(e_rmse)
 
 
+def test_ransac_draw_one_past_the_field_is_dropped(seg, oracle):
+    """Pins the one deliberate deviation of the RANSAC restatement: the reference draws subset indices
+    from [0, n] INCLUSIVE (libs/motion.cpp:208) and, when n comes up, reads one element past the motion
+    field -- undefined behaviour.  Here that iteration is dropped after consuming the same draws.  With
+    5-vector fields a draw of n happens in most calls (7 iterations x 1/6 each).  The checker stores a
+    far-away vector in the slot the reference over-reads, so such an iteration has exactly one inlier-free
+    subset mean and can only win while nothing else has been evaluated; every call whose winning subset
+    is inside the field must then agree bit for bit, call after call (the engine state stays in step)."""
+    import ctypes as C
+    L = _need_ref(oracle, 99)
+    state, hit, agree = 99, 0, 0
+    for call in range(60):
+        rng = np.random.default_rng(call)
+        mv = rng.integers(-3, 4, size=(5, 2)).astype(np.float32)
+        n = mv.shape[0]
+        buf = np.zeros((n + 1, 2), np.float32)
+        buf[:n] = mv
+        buf[n] = 1.0e6  # what the reference reads when it draws n: no vector is within 7.5 of it
+        rm, ni = C.c_float(), C.c_uint32()
+        gm = np.zeros(2, np.float32)
+        inl = np.zeros(n, np.uint32)
+        f32p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+        L.ref_ransac(buf.ctypes.data_as(f32p), n, 1, C.c_float(7.5), C.c_float(0.99), C.c_float(0.5), C.byref(rm),
+                     gm.ctypes.data_as(f32p), inl.ctypes.data_as(u32p), C.byref(ni))
+        rmse, g, i2, state = seg.ransac(mv, 1, 7.5, 0.99, 0.5, rng_state=state)
+        if abs(gm).max() > 1e5:  # the over-read slot won in the reference (every earlier draw was n too)
+            hit += 1
+            continue
+        agree += 1
+        assert np.array_equal(i2, inl[:ni.value]) and np.array_equal(g, gm) and np.float32(rmse) == np.float32(rm.value)
+    assert agree >= 50
+
+
 def test_ransac_degenerate_no_consensus(seg, oracle):
     """inlier_thresh 0: no vector is ever an inlier; the reference then reports the rmse of the last
     subset against the CALLER's global_motion value (libs/motion.cpp:239-241)."""

@@ -1,6 +1,16 @@
-O=gpurun_out/r2o; mkdir -p $O
-timeout 1500 python -m pytest tests -m gpu -x -q -k "session or encoder or app or c1 or c4 or stream or shard" > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
-tail -3 $O/pytest.log
-python bench.py --no-cpu --no-sad --steps 5 2>/dev/null | python -c "
-import json,sys
-b=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value', b['value'], 'e2e', {k:b['e2e'][k] for k in ('value','frac','ms_per_step')}, b['e2e']['copy_only_ceiling']['value'], b['parity']['ok'])"
+O=gpurun_out/r2final; mkdir -p $O
+nvidia-smi --query-gpu=name,driver_version --format=csv,noheader > $O/gpu.txt; nproc >> $O/gpu.txt
+timeout 2400 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log; tail -3 $O/pytest.log
+timeout 600 python bench.py > $O/bench_final.json 2> $O/bench_final.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_ref.err
+timeout 300 python bench.py --width 960 --height 540 --frames 30 --batch 30 --steps 20 --warmup 3 > $O/bench_c1.json 2> $O/bench_c1.err; echo "c1 rc=$?"
+timeout 300 python bench.py --impl reference --width 960 --height 540 --frames 30 --steps 5 --warmup 1 > $O/bench_c1_reference_arm.json 2>> $O/bench_c1.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-sad --no-parity > $O/ncu_launch.log 2>&1
+NCU="ncu --set full --clock-control none --import-source on"
+$NCU -k "regex:dct8x8|pyr_down|hbma_tile" -s 12 -c 4 -o $O/step_kernels python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-sad --no-parity > $O/n2.log 2>&1
+$NCU -k regex:hbma_rs -s 2 -c 2 -o $O/rs_R16L2 python tools/sweep_hbma.py --ranges 16 --levels 2 --cpu-budget-gabsdiff 0 --out $O/sw_ncu > $O/n3.log 2>&1
+$NCU -k "regex:hbma_rs|hbma_ebma_tile" -s 4 -c 4 -o $O/rs_R64L4 python tools/sweep_hbma.py --ranges 64 --levels 4 --cpu-budget-gabsdiff 0 --out $O/sw_ncu > $O/n4.log 2>&1
+python tools/sweep_hbma.py --out $O/sweep_hbma_v13 > $O/sweep.log 2>&1
+for tb in 8 16 4; do python tools/microbench.py --tb $tb --out $O/microbench_4k_tb$tb.json > $O/mb$tb.log 2>&1; done
+python tools/compat_bench.py > $O/compat.json 2> $O/compat.err
+ls $O; tail -c 600 $O/bench_final.json
