@@ -1,16 +1,13 @@
-O=gpurun_out/r2final; mkdir -p $O
-nvidia-smi --query-gpu=name,driver_version --format=csv,noheader > $O/gpu.txt; nproc >> $O/gpu.txt
-timeout 2400 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log; tail -3 $O/pytest.log
-timeout 600 python bench.py > $O/bench_final.json 2> $O/bench_final.err; echo "bench rc=$?"
-timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_ref.err
+O=gpurun_out/r2q; mkdir -p $O
 timeout 300 python bench.py --width 960 --height 540 --frames 30 --batch 30 --steps 20 --warmup 3 > $O/bench_c1.json 2> $O/bench_c1.err; echo "c1 rc=$?"
-timeout 300 python bench.py --impl reference --width 960 --height 540 --frames 30 --steps 5 --warmup 1 > $O/bench_c1_reference_arm.json 2>> $O/bench_c1.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-sad --no-parity > $O/ncu_launch.log 2>&1
-NCU="ncu --set full --clock-control none --import-source on"
-$NCU -k "regex:dct8x8|pyr_down|hbma_tile" -s 12 -c 4 -o $O/step_kernels python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-sad --no-parity > $O/n2.log 2>&1
-$NCU -k regex:hbma_rs -s 2 -c 2 -o $O/rs_R16L2 python tools/sweep_hbma.py --ranges 16 --levels 2 --cpu-budget-gabsdiff 0 --out $O/sw_ncu > $O/n3.log 2>&1
-$NCU -k "regex:hbma_rs|hbma_ebma_tile" -s 4 -c 4 -o $O/rs_R64L4 python tools/sweep_hbma.py --ranges 64 --levels 4 --cpu-budget-gabsdiff 0 --out $O/sw_ncu > $O/n4.log 2>&1
-python tools/sweep_hbma.py --out $O/sweep_hbma_v13 > $O/sweep.log 2>&1
-for tb in 8 16 4; do python tools/microbench.py --tb $tb --out $O/microbench_4k_tb$tb.json > $O/mb$tb.log 2>&1; done
-python tools/compat_bench.py > $O/compat.json 2> $O/compat.err
-ls $O; tail -c 600 $O/bench_final.json
+timeout 300 python bench.py --impl reference --width 960 --height 540 --frames 30 --batch 30 --steps 10 --warmup 1 > $O/bench_c1_reference_arm.json 2>> $O/bench_c1.err
+timeout 300 python bench.py --impl reference --width 960 --height 540 --frames 30 --batch 30 --steps 10 --warmup 1 2>/dev/null | head -c 0
+taskset -c 0 python bench.py --impl reference --width 960 --height 540 --frames 30 --batch 30 --steps 3 --warmup 1 > $O/bench_c1_reference_arm_1core.json 2>> $O/bench_c1.err
+taskset -c 0 python bench.py --impl reference --steps 1 --warmup 0 --frames 31 > $O/bench_c2_reference_arm_1core.json 2>> $O/bench_c1.err
+python - <<'P'
+import json
+O='gpurun_out/r2q/'
+for f in ('bench_c1.json','bench_c1_reference_arm.json','bench_c1_reference_arm_1core.json','bench_c2_reference_arm_1core.json'):
+    b=json.loads(open(O+f).read().strip().splitlines()[-1])
+    print(f, b['config']['workload'][:45], 'value', round(b['value'],1), 'e2e', b['e2e'] and round(b['e2e']['value'],1), 'cores', b['cpu_baseline'] and b['cpu_baseline']['cores'], 'parity', b.get('parity') and b['parity']['ok'])
+P
