@@ -51,6 +51,21 @@ def test_y_pyramid_fused_upper_levels_vs_oracle(gpu, oracle, w, h, L):
         assert np.array_equal(got[l], exp[l]), l
 
 
+def test_y_pyramid_fused_levels_many_tiles_per_cta(gpu, oracle):
+    """A 24-frame batch of random 1080p frames (2 160 tiles of pyr_down2_kernel, 3 672 of the level-0
+    kernel): every level of every pyramid matters for the vectors of random content."""
+    w, h, n = 1920, 1080, 24
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, max_batch=n)) as s:
+        mv, mad, _ = s.encode(frames, want_stream=False)
+        pw, ph = s.padded_w, s.padded_h
+    pyr = [oracle.y_pyramid(f, pw, ph, 4) for f in frames]
+    for i in range(1, n):  # random frames: every level of both pyramids matters for the vectors
+        emv, emad = oracle.hbma(pyr[i - 1], pyr[i], 8)
+        assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad), i
+
+
 def test_y_pyramid_fused_levels_in_a_batch(gpu, oracle):
     """The session path: pyramids of a whole batch (slot stride, first_slot = 1) feed the search."""
     w, h, n = 432, 248, 7

@@ -1,13 +1,8 @@
-O=gpurun_out/r2q; mkdir -p $O
-timeout 300 python bench.py --width 960 --height 540 --frames 30 --batch 30 --steps 20 --warmup 3 > $O/bench_c1.json 2> $O/bench_c1.err; echo "c1 rc=$?"
-timeout 300 python bench.py --impl reference --width 960 --height 540 --frames 30 --batch 30 --steps 10 --warmup 1 > $O/bench_c1_reference_arm.json 2>> $O/bench_c1.err
-timeout 300 python bench.py --impl reference --width 960 --height 540 --frames 30 --batch 30 --steps 10 --warmup 1 2>/dev/null | head -c 0
-taskset -c 0 python bench.py --impl reference --width 960 --height 540 --frames 30 --batch 30 --steps 3 --warmup 1 > $O/bench_c1_reference_arm_1core.json 2>> $O/bench_c1.err
-taskset -c 0 python bench.py --impl reference --steps 1 --warmup 0 --frames 31 > $O/bench_c2_reference_arm_1core.json 2>> $O/bench_c1.err
-python - <<'P'
-import json
-O='gpurun_out/r2q/'
-for f in ('bench_c1.json','bench_c1_reference_arm.json','bench_c1_reference_arm_1core.json','bench_c2_reference_arm_1core.json'):
-    b=json.loads(open(O+f).read().strip().splitlines()[-1])
-    print(f, b['config']['workload'][:45], 'value', round(b['value'],1), 'e2e', b['e2e'] and round(b['e2e']['value'],1), 'cores', b['cpu_baseline'] and b['cpu_baseline']['cores'], 'parity', b.get('parity') and b['parity']['ok'])
-P
+O=gpurun_out/r2p; mkdir -p $O
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_baseline_configs.py -m gpu -x -q -k "pyramid or session or c1" > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
+tail -3 $O/pytest.log
+python bench.py --no-cpu --no-sad --no-e2e 2>/dev/null | python -c "
+import json,sys
+b=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value', b['value'], b['ms_per_step'], {k:(round(v['gbs']), v.get('ms_per_launch', v.get('ms_per_launch_group'))) for k,v in b['stages'].items()}, b['parity']['ok'])"
+ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:pyr_down" -s 6 -c 4 --csv --log-file $O/pyr_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-sad --no-parity > $O/n1.log 2>&1
+grep pyr_down $O/pyr_launches.csv | cut -d, -f5,14- | cut -c1-40,150- | tail -4
