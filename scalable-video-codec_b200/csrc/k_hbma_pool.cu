@@ -1079,16 +1079,11 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int
   }
   if (p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > (L == 1 ? 112u : 64u)) return false;
   if ((uint64_t)p.mvw * p.mvh * p.n_frames > 0x7fffffffull) return false;
-  if (L >= 2 && r <= 8 && !force && rs_level_supported(p)) {
-    // windows of at most 17 x 17 candidates: one launch per level.  Refinement levels and an 8x8 top
-    // level realign their windows in registers (k_hbma_rs.cu); a top level of 4x4 or smaller blocks has
-    // so little SAD work per candidate that the shared window of the tile kernel wins.
-    const uint32_t top = L - 1;
-    if (L == 2) *err = launch_rs_level(p, top, true, st);
-    else if (L == 3) *err = launch_top_tile<8, 80 / 4, 17, 256, 3, 4>(p, top, st);
-    else if (L == 4) *err = launch_top_tile<8, 80 / 2, 17, 256, 3, 2>(p, top, st);
-    else *err = launch_top_tile<8, 80, 17, 256, 3, 1>(p, top, st);
-    for (int l = (int)L - 2; l >= 0 && *err == cudaSuccess; --l) *err = launch_rs_level(p, (uint32_t)l, false, st);
+  if (r <= 8 && !force && rs_level_supported(p)) {
+    // windows of at most 17 x 17 candidates (r = 5..8): one launch per level, windows realigned in
+    // registers (k_hbma_rs.cu); the top level -- or the only one: L = 1, plain EBMA -- with the "<=" scan
+    // rule.  (r = 3, 4 stay on the bounded-reach tile kernel: 41-50 % of the SAD peak against 30-35 % here.)
+    for (int l = (int)L - 1; l >= 0 && *err == cudaSuccess; --l) *err = launch_rs_level(p, (uint32_t)l, l == (int)L - 1, st);
     if (extra_launches) *extra_launches += (int)L - 1;  // the caller counts one
     return true;
   }

@@ -29,8 +29,10 @@
 //   inside a persistent CTA: -20 %; warps uniform in the chunk index (a 5-row instance for the short
 //   chunk): the 8 windows a warp then reads lie 128-byte aligned in shared memory -> bank conflicts, -20 %;
 //   16 / 32 blocks per CTA for the small levels: 263 / 186; windows staged by 16-byte global loads
-//   instead of TMA: 613 / 248 / 140.  ncu of the final 16x16 level: ALU pipe 85 % busy, 64 % of all
-//   instructions are VABSDIFF4, 7 % SHF (profiles/r02_ncu_hbma_rs_*.txt).
+//   instead of TMA: 613 / 248 / 140; windows of 9 x 9 (r = 3, 4) on these kernels: 30-35 % of the SAD
+//   peak against 41-50 % on the bounded-reach tile kernel, which keeps them.  ncu of the final 16x16
+//   level: ALU pipe 84-87 % busy, 64 % of all instructions are VABSDIFF4, 7 % SHF
+//   (profiles/r02_ncu_hbma_rs_*.txt).
 #include <float.h>
 
 #include "common.cuh"
@@ -109,31 +111,40 @@ __device__ __forceinline__ void rs_item(const uint8_t* __restrict__ trow, const 
   }
 }
 
-// keys of one item into the block's running minimum (+ the SADs themselves at the top level)
+// keys of one item into the block's running minimum.  Top level: also returns whether the SADs of this
+// item alone already increase somewhere along the scan order (later row, or later column of the same row):
+// a sequence that never increases cannot contain ANY later element above an earlier one, so such a pair
+// proves that not every candidate updated the minimum (libs/motion.cpp:333-337) without looking at the
+// neighbouring items.
 template <int NC, int NDY, bool TOP>
-__device__ __forceinline__ void rs_commit(const uint32_t (&acc)[NC][NDY], const RsLv& v, const int col0,
-                                          const int dy0, uint32_t* best, uint16_t* sads) {
+__device__ __forceinline__ bool rs_commit(const uint32_t (&acc)[NC][NDY], const RsLv& v, const int col0,
+                                          const int dy0, const int nc, uint32_t* best) {
   const int ndy = min(v.csz, v.ncy - dy0);
   uint32_t key = 0xffffffffu;
+  bool viol = false;
+  uint32_t prev = 0xffffffffu;
+  uint32_t idx_row = (uint32_t)(dy0 * v.ncx + col0);  // scan order inside the clamped window
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const int col = col0 + 4 * i;
-    if (col < v.ncx) {
+  for (int d = 0; d < NDY; ++d) {
+    if (d < ndy) {
 #pragma unroll
-      for (int d = 0; d < NDY; ++d) {
-        if (d < ndy) {
-          const uint32_t idx = (uint32_t)((dy0 + d) * v.ncx + col);  // scan order inside the clamped window
+      for (int i = 0; i < NC; ++i) {
+        if (i < nc && col0 + 4 * i < v.ncx) {
+          const uint32_t idx = idx_row + 4u * i;
           if (TOP) {
-            sads[idx] = (uint16_t)acc[i][d];
             key = min(key, acc[i][d] * 65536u + (0xffffu - idx));  // "<=": the last minimum wins
+            viol |= acc[i][d] > prev;
+            prev = acc[i][d];
           } else {
             key = min(key, acc[i][d] * 65536u + idx);              // "<": the first minimum wins
           }
         }
       }
     }
+    idx_row += (uint32_t)v.ncx;
   }
   if (key != 0xffffffffu) atomicMin(best, key);
+  return viol;
 }
 
 template <int B, int NDY, int NB>
@@ -240,7 +251,12 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
     }
   }
   // ---- work items: static lane -> (block, byte phase, chunk) ----------------------------------
-  int it_j = -1, it_col0 = 0, it_dy0 = 0, it_nc = 0;  // this lane's item (the top level re-reads it below)
+  int it_j = -1, it_col0 = 0, it_dy0 = 0, it_nc = 0;  // this lane's item
+  uint32_t acc[NC][NDY];
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+#pragma unroll
+    for (int d = 0; d < NDY; ++d) acc[i][d] = 0;
   if (tid < MAIN) {
     const int j = tid / (4 * NCH), rem = tid - j * (4 * NCH);
     const int ph = rem / NCH, c = rem - ph * NCH;
@@ -250,14 +266,8 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
       it_j = j; it_col0 = ph; it_dy0 = dy0; it_nc = NC;
       const uint8_t* blk = smem + j * G::BLK;
       const int sx = v.sxb + ph;
-      uint32_t acc[NC][NDY];
-#pragma unroll
-      for (int i = 0; i < NC; ++i)
-#pragma unroll
-        for (int d = 0; d < NDY; ++d) acc[i][d] = 0;
       rs_item<B, NC, NDY, G::PA>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, smem + G::OFF_ANC + v.aoff, acc);
-      rs_commit<NC, NDY, TOP>(acc, v, ph, dy0, &sBest[j],
-                              reinterpret_cast<uint16_t*>(smem + G::OFF_SADS) + j * (G::SADS / 2));
+      if (rs_commit<NC, NDY, TOP>(acc, v, ph, dy0, NC, &sBest[j])) sViol[j] = 1u;
     }
   } else if (LAST) {
     const int l = tid - MAIN;
@@ -269,36 +279,50 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
         it_j = j; it_col0 = 4 * NC; it_dy0 = dy0; it_nc = 1;
         const uint8_t* blk = smem + j * G::BLK;
         const int sx = v.sxb + 4 * NC;
-        uint32_t acc[1][NDY];
+        uint32_t a1[1][NDY];
 #pragma unroll
-        for (int d = 0; d < NDY; ++d) acc[0][d] = 0;
-        rs_item<B, 1, NDY, G::PA>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, smem + G::OFF_ANC + v.aoff, acc);
-        rs_commit<1, NDY, TOP>(acc, v, 4 * NC, dy0, &sBest[j],
-                               reinterpret_cast<uint16_t*>(smem + G::OFF_SADS) + j * (G::SADS / 2));
+        for (int d = 0; d < NDY; ++d) a1[0][d] = 0;
+        rs_item<B, 1, NDY, G::PA>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, smem + G::OFF_ANC + v.aoff, a1);
+#pragma unroll
+        for (int d = 0; d < NDY; ++d) acc[0][d] = a1[0][d];
+        if (rs_commit<NC, NDY, TOP>(acc, v, 4 * NC, dy0, 1, &sBest[j])) sViol[j] = 1u;
       }
     }
   }
   __syncthreads();
   if (TOP) {
     // "every candidate updated the minimum" <=> the SADs never increase along the scan order of the
-    // clamped window (libs/motion.cpp:312-337): every lane compares its candidates with their
-    // scan-order predecessors
-    if (it_j >= 0 && sViol[it_j] == 0u) {
-      const RsLv v = sLv[it_j];
-      const uint16_t* sd = reinterpret_cast<const uint16_t*>(smem + G::OFF_SADS) + it_j * (G::SADS / 2);
+    // clamped window (libs/motion.cpp:312-337).  Nearly every block has been settled by the in-item test
+    // above; the rest (flat or saturated content) exchange their SADs through shared memory and every
+    // lane compares its candidates with their scan-order predecessors.
+    const bool need = it_j >= 0 && sViol[it_j] == 0u;
+    if (__syncthreads_or(need)) {  // CTA-uniform
+      uint16_t* sd = reinterpret_cast<uint16_t*>(smem + G::OFF_SADS) + (it_j >= 0 ? it_j : 0) * (G::SADS / 2);
+      const RsLv v = sLv[it_j >= 0 ? it_j : 0];
       const int ndy = min(v.csz, v.ncy - it_dy0);
-      bool viol = false;
-      for (int i = 0; i < it_nc; ++i) {
-        const int col = it_col0 + 4 * i;
-        if (col < v.ncx)
-          for (int d = 0; d < ndy; ++d) {
-            const int idx = (it_dy0 + d) * v.ncx + col;
-            if (idx > 0 && sd[idx] > sd[idx - 1]) viol = true;
-          }
+      if (need) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+          if (i < it_nc && it_col0 + 4 * i < v.ncx)
+#pragma unroll
+            for (int d = 0; d < NDY; ++d)
+              if (d < ndy) sd[(it_dy0 + d) * v.ncx + it_col0 + 4 * i] = (uint16_t)acc[i][d];
       }
-      if (viol) sViol[it_j] = 1u;
+      __syncthreads();
+      if (need) {
+        bool viol = false;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+          if (i < it_nc && it_col0 + 4 * i < v.ncx)
+#pragma unroll
+            for (int d = 0; d < NDY; ++d) {
+              const int idx = (it_dy0 + d) * v.ncx + it_col0 + 4 * i;
+              if (d < ndy && idx > 0 && acc[i][d] > sd[idx - 1]) viol = true;
+            }
+        if (viol) sViol[it_j] = 1u;
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   if (own) {  // tid < NB
     const uint32_t best = sBest[tid];
