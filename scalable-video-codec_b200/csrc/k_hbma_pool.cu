@@ -1079,10 +1079,11 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int
   }
   if (p.bw != 16 || p.bh != 16 || L > 5 || r < 5 || r > (L == 1 ? 112u : 64u)) return false;
   if ((uint64_t)p.mvw * p.mvh * p.n_frames > 0x7fffffffull) return false;
-  if (r <= 8 && !force && rs_level_supported(p)) {
-    // windows of at most 17 x 17 candidates (r = 5..8): one launch per level, windows realigned in
-    // registers (k_hbma_rs.cu); the top level -- or the only one: L = 1, plain EBMA -- with the "<=" scan
-    // rule.  (r = 3, 4 stay on the bounded-reach tile kernel: 41-50 % of the SAD peak against 30-35 % here.)
+  if (r <= 16 && (L >= 2 || r <= 8) && !force && rs_level_supported(p)) {
+    // windows of at most 33 x 33 candidates (r = 5..16): one launch per level, windows realigned in
+    // registers (k_hbma_rs.cu); the top level -- or the only one, r <= 8: L = 1, plain EBMA -- with the
+    // "<=" scan rule.  (r = 3, 4 stay on the bounded-reach tile kernel: 41-50 % of the SAD peak against
+    // 30-35 % here; L = 1 with r = 9..16 on the shared-window tile kernel below: 69 %.)
     for (int l = (int)L - 1; l >= 0 && *err == cudaSuccess; --l) *err = launch_rs_level(p, (uint32_t)l, l == (int)L - 1, st);
     if (extra_launches) *extra_launches += (int)L - 1;  // the caller counts one
     return true;
@@ -1090,8 +1091,7 @@ bool try_launch_pool(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int
   if (L >= 2 && r <= 32 && p.mv && p.mad && !force) {
     // one launch per level; <range class, candidate rows per item, blocks per CTA and CTAs per SM of
     // the 16x16 refinement level>
-    if (r <= 16) *err = launch_levels<16, 11, 3, 128, 4>(p, st, extra_launches);
-    else *err = launch_levels<32, 13, 2, 128, 3>(p, st, extra_launches);
+    *err = launch_levels<32, 13, 2, 128, 3>(p, st, extra_launches);  // r = 17..32
     return true;
   }
   // <range class, ..., candidate rows per item, threads, CTAs per SM>: measured best of several shapes

@@ -42,7 +42,12 @@ namespace svc {
 
 namespace {
 
-constexpr int kRsPT = 48;  // window pitch = TMA box width: 15 (16-byte origin) + 2*8 + 16 + 1 word of shift slack
+// window pitch = TMA box width.  The box starts at the 16-byte boundary below the window (<= 15 bytes of
+// slack); the last candidate column starts at most at byte 15 + 2r, its aligned word at 12 + 2r (2r a
+// multiple of 4 for the classes used), and an item reads B/4 + 1 words from there: 32 + 2r bytes in all.
+// (64 bytes would do for r <= 16, but chunks of 6 rows at a pitch of 16 words all start in the same bank:
+// the lanes of a block -- one per chunk -- would conflict 6 ways; 80 spreads them)
+__host__ __device__ constexpr int rs_pitch(int rmax) { return rmax > 8 ? 80 : (32 + 2 * rmax + 15) & ~15; }  // 48 / 80
 
 struct RsLv {        // one motion block at this level
   int x0, y0;        // origin of the clamped candidate window
@@ -60,7 +65,7 @@ struct RsLv {        // one motion block at this level
 // per trip.  The body is NDY x (one window row in, one anchor row in, NC x NDY x NW SADs): a few KB of
 // code that stays in the instruction cache (the straight-line version of a 16x16 item is ~30 KB and
 // measured 5 % slower: `no_instruction` stalls).
-template <int B, int NC, int NDY, int PA>  // PA: pitch of the anchor tile
+template <int B, int NC, int NDY, int PA, int PT>  // PA: pitch of the anchor tile, PT: of the window
 __device__ __forceinline__ void rs_item(const uint8_t* __restrict__ trow, const uint32_t sh,
                                         const uint8_t* __restrict__ ablk, uint32_t (&acc)[NC][NDY]) {
   constexpr int NW = B >= 4 ? B / 4 : 1;
@@ -76,15 +81,15 @@ __device__ __forceinline__ void rs_item(const uint8_t* __restrict__ trow, const 
     for (int k = 0; k < NS; ++k) dst[k] = __funnelshift_r(raw[k], raw[k + 1], sh) & MASK;
   };
 #pragma unroll
-  for (int d = 0; d < NDY - 1; ++d) load_row(trow + d * kRsPT, S[d]);
+  for (int d = 0; d < NDY - 1; ++d) load_row(trow + d * PT, S[d]);
 #pragma unroll 1
   for (int ar0 = 0; ar0 < B; ar0 += NDY) {
-    const uint8_t* tp = trow + (ar0 + NDY - 1) * kRsPT;
+    const uint8_t* tp = trow + (ar0 + NDY - 1) * PT;
     const uint8_t* ap = ablk + ar0 * PA;
 #pragma unroll
     for (int u = 0; u < NDY; ++u) {
       if (ar0 + u < B) {  // uniform
-        load_row(tp + u * kRsPT, S[(u + NDY - 1) % NDY]);  // window row ar0 + u + NDY - 1
+        load_row(tp + u * PT, S[(u + NDY - 1) % NDY]);  // window row ar0 + u + NDY - 1
         uint32_t a[NW];
         const uint8_t* q = ap + u * PA;
         if constexpr (B == 16) {
@@ -147,16 +152,18 @@ __device__ __forceinline__ bool rs_commit(const uint32_t (&acc)[NC][NDY], const 
   return viol;
 }
 
-template <int B, int NDY, int NB>
+template <int B, int NDY, int NB, int RMAX>
 struct RsGeom {
-  static constexpr int ROWS = B + 16 + NDY;                       // + slack rows a short last chunk streams
-  static constexpr int WIN = (kRsPT * ROWS + 127) & ~127;
+  static constexpr int PT = rs_pitch(RMAX);
+  static constexpr int NCAND = (2 * RMAX + 1) * (2 * RMAX + 1);
+  static constexpr int ROWS = B + 2 * RMAX + NDY;                 // + slack rows a short last chunk streams
+  static constexpr int WIN = (PT * ROWS + 127) & ~127;
   static constexpr int BLK = WIN;                                 // one window per block
   // the NB blocks of a CTA are horizontal neighbours: ONE anchor tile (one TMA request instead of NB)
   static constexpr int PA = (NB * B) % 16 == 0 ? NB * B : ((NB * B + 15 + 15) & ~15);  // (+ 16-byte origin slack)
   static constexpr int OFF_ANC = NB * BLK;
   static constexpr int ANC = (PA * B + 127) & ~127;
-  static constexpr int SADS = 17 * 17 * 2 + 2;                    // u16 per candidate (top level only)
+  static constexpr int SADS = NCAND * 2 + 2;                      // u16 per candidate (top level only)
   static constexpr int OFF_SADS = OFF_ANC + ANC;
 };
 
@@ -164,11 +171,13 @@ struct RsGeom {
 // refinement of the vector / MAD found in p.mv / p.mad; NC columns per item, NDY rows per chunk, NCH
 // chunks per window, NB blocks per CTA; LAST: a full window has a 17th column (r = 8), searched by
 // 1-column items on an extra warp.
-template <int B, bool TOP, int NC, int NDY, int NCH, int NB, bool LAST, int MINB>
-__global__ void __launch_bounds__(NB * 4 * NCH + (LAST ? (NB * NCH + 31) / 32 * 32 : 0), MINB)
+// KG groups of NC columns per byte phase (1: windows up to 17 wide, 2: up to 33), RMAX: largest range.
+template <int B, bool TOP, int NC, int NDY, int NCH, int NB, bool LAST, int MINB, int KG, int RMAX>
+__global__ void __launch_bounds__(NB * 4 * KG * NCH + (LAST ? (NB * NCH + 31) / 32 * 32 : 0), MINB)
 hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ HbmaParams p, const int lvl) {
-  using G = RsGeom<B, NDY, NB>;
-  constexpr int MAIN = NB * 4 * NCH;
+  using G = RsGeom<B, NDY, NB, RMAX>;
+  constexpr int kRsPT = G::PT;
+  constexpr int MAIN = NB * 4 * KG * NCH;
   static_assert(MAIN % 32 == 0, "main items must fill whole warps");
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -258,16 +267,18 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
 #pragma unroll
     for (int d = 0; d < NDY; ++d) acc[i][d] = 0;
   if (tid < MAIN) {
-    const int j = tid / (4 * NCH), rem = tid - j * (4 * NCH);
-    const int ph = rem / NCH, c = rem - ph * NCH;
+    const int j = tid / (4 * KG * NCH), rem = tid - j * (4 * KG * NCH);
+    const int ph = rem / (KG * NCH), rem2 = rem - ph * (KG * NCH);
+    const int kg = rem2 / NCH, c = rem2 - kg * NCH;
+    const int col0 = ph + 4 * NC * kg;  // columns col0, col0 + 4, .. of byte phase ph
     const RsLv v = sLv[j];
     const int dy0 = c * v.csz;
-    if (ph < v.ncx && dy0 < v.ncy) {
-      it_j = j; it_col0 = ph; it_dy0 = dy0; it_nc = NC;
+    if (col0 < v.ncx && dy0 < v.ncy) {
+      it_j = j; it_col0 = col0; it_dy0 = dy0; it_nc = NC;
       const uint8_t* blk = smem + j * G::BLK;
-      const int sx = v.sxb + ph;
-      rs_item<B, NC, NDY, G::PA>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, smem + G::OFF_ANC + v.aoff, acc);
-      if (rs_commit<NC, NDY, TOP>(acc, v, ph, dy0, NC, &sBest[j])) sViol[j] = 1u;
+      const int sx = v.sxb + col0;
+      rs_item<B, NC, NDY, G::PA, kRsPT>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, smem + G::OFF_ANC + v.aoff, acc);
+      if (rs_commit<NC, NDY, TOP>(acc, v, col0, dy0, NC, &sBest[j])) sViol[j] = 1u;
     }
   } else if (LAST) {
     const int l = tid - MAIN;
@@ -275,17 +286,17 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
     if (j < NB) {
       const RsLv v = sLv[j];
       const int dy0 = c * v.csz;
-      if (v.ncx > 4 * NC && dy0 < v.ncy) {  // the window has a column 4*NC (= 16)
-        it_j = j; it_col0 = 4 * NC; it_dy0 = dy0; it_nc = 1;
+      if (v.ncx > 4 * NC * KG && dy0 < v.ncy) {  // the window has a column 4*NC*KG (= 16 or 32)
+        it_j = j; it_col0 = 4 * NC * KG; it_dy0 = dy0; it_nc = 1;
         const uint8_t* blk = smem + j * G::BLK;
-        const int sx = v.sxb + 4 * NC;
+        const int sx = v.sxb + 4 * NC * KG;
         uint32_t a1[1][NDY];
 #pragma unroll
         for (int d = 0; d < NDY; ++d) a1[0][d] = 0;
-        rs_item<B, 1, NDY, G::PA>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, smem + G::OFF_ANC + v.aoff, a1);
+        rs_item<B, 1, NDY, G::PA, kRsPT>(blk + dy0 * kRsPT + (sx & ~3), (uint32_t)(sx & 3) * 8u, smem + G::OFF_ANC + v.aoff, a1);
 #pragma unroll
         for (int d = 0; d < NDY; ++d) acc[0][d] = a1[0][d];
-        if (rs_commit<NC, NDY, TOP>(acc, v, 4 * NC, dy0, 1, &sBest[j])) sViol[j] = 1u;
+        if (rs_commit<NC, NDY, TOP>(acc, v, 4 * NC * KG, dy0, 1, &sBest[j])) sViol[j] = 1u;
       }
     }
   }
@@ -347,11 +358,12 @@ hbma_rs_kernel(const __grid_constant__ EbmaMaps maps, const __grid_constant__ Hb
   }
 }
 
-template <int B, bool TOP, int NC, int NDY, int NCH, int NB, bool LAST, int MINB>
+template <int B, bool TOP, int NC, int NDY, int NCH, int NB, bool LAST, int MINB, int KG = 1, int RMAX = 8>
 cudaError_t launch_rs(const HbmaParams& p, uint32_t lvl, cudaStream_t st) {
-  using G = RsGeom<B, NDY, NB>;
+  using G = RsGeom<B, NDY, NB, RMAX>;
+  constexpr int kRsPT = G::PT;
   constexpr int SMEM = G::OFF_SADS + (TOP ? NB * G::SADS : 0);
-  constexpr int THREADS = NB * 4 * NCH + (LAST ? (NB * NCH + 31) / 32 * 32 : 0);
+  constexpr int THREADS = NB * 4 * KG * NCH + (LAST ? (NB * NCH + 31) / 32 * 32 : 0);
   EbmaMaps maps;
   const uint32_t n_slots = p.n_frames + 1;
   const uint8_t* base = p.pyr + p.lay.off[lvl];
@@ -360,7 +372,7 @@ cudaError_t launch_rs(const HbmaParams& p, uint32_t lvl, cudaStream_t st) {
       !encode_box(&maps.a, base, p.lay.w[lvl], p.lay.h[lvl], p.lay.pitch[lvl], p.lay.slot_bytes, n_slots, G::PA, B))
     return cudaErrorNotSupported;
   static_assert(G::PA <= 256, "TMA box limit");
-  auto kern = hbma_rs_kernel<B, TOP, NC, NDY, NCH, NB, LAST, MINB>;
+  auto kern = hbma_rs_kernel<B, TOP, NC, NDY, NCH, NB, LAST, MINB, KG, RMAX>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   if (e != cudaSuccess) return e;
   const uint64_t n_ctas = (uint64_t)((p.mvw + NB - 1) / NB) * p.mvh * p.n_frames;
@@ -376,6 +388,8 @@ cudaError_t launch_rs(const HbmaParams& p, uint32_t lvl, cudaStream_t st) {
 template <int B, bool TOP>
 cudaError_t launch_rs_class(const HbmaParams& p, uint32_t lvl, cudaStream_t st) {
   constexpr int MINB = B == 16 ? 5 : 6;
+  // r = 9..16 -> windows up to 33 x 33: two groups of 4 columns per byte phase, 6 chunks, 2 blocks per CTA
+  if (p.r >= 9) return launch_rs<B, TOP, 4, 6, 6, 2, true, MINB, 2, 16>(p, lvl, st);
   if (p.r >= 5) return launch_rs<B, TOP, 4, 6, 3, 8, true, MINB>(p, lvl, st);
   return launch_rs<B, TOP, 3, 5, 2, 16, false, MINB>(p, lvl, st);
 }
@@ -383,7 +397,7 @@ cudaError_t launch_rs_class(const HbmaParams& p, uint32_t lvl, cudaStream_t st) 
 }  // namespace
 
 bool rs_level_supported(const HbmaParams& p) {
-  return p.bw == 16 && p.bh == 16 && p.r >= 3 && p.r <= 8 && p.mv && p.mad && p.lay.levels <= 5 &&
+  return p.bw == 16 && p.bh == 16 && p.r >= 3 && p.r <= 16 && p.mv && p.mad && p.lay.levels <= 5 &&
          (uint64_t)p.mvw * p.mvh * p.n_frames <= 0x7fffffffull;
 }
 
