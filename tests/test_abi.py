@@ -83,6 +83,35 @@ def test_session_config_validation_mirrors_reference_messages(svc):
         assert e.value.code == 1 and msg in str(e.value), (kw, str(e.value))
 
 
+def test_session_config_struct_size_versions_the_struct(svc):
+    """struct_size versions svc_session_config: a caller compiled against the round-1 header (no
+    hbma_kernel_family / host_chunk_frames) is accepted with those fields zero; sizes that match no
+    version and unknown kernel families are argument errors."""
+    from svc_b200.binding import _Cfg
+    L = svc.lib()
+    old_size = _Cfg.hbma_kernel_family.offset
+
+    def create(struct_size, family=0, w=64):
+        c = _Cfg(struct_size, w, 64, 16, 16, 8, 4, 8, 8, 0, 0, None, family, 0)
+        h = C.c_void_p()
+        rc = L.svc_session_create(C.byref(c), C.byref(h))
+        msg = L.svc_last_error().decode()
+        if rc == 0:
+            L.svc_session_destroy(h)
+        return rc, msg
+
+    for size in (old_size, C.sizeof(_Cfg)):
+        rc, msg = create(size, w=0)  # passes the size check, then fails on the frame width
+        assert rc == 1 and "frame dimensions" in msg, (size, msg)
+    for size in (old_size - 4, C.sizeof(_Cfg) + 8, 0):
+        rc, msg = create(size)
+        assert rc == 1 and "struct_size" in msg, (size, msg)
+    rc, msg = create(C.sizeof(_Cfg), family=9)
+    assert rc == 1 and "hbma_kernel_family" in msg
+    rc, msg = create(old_size, family=9)  # the field lies beyond the declared size: ignored
+    assert "hbma_kernel_family" not in msg
+
+
 def test_no_device_is_a_hard_error_not_a_fallback(svc):
     if svc.device_count() > 0:
         pytest.skip("a CUDA device is visible")
