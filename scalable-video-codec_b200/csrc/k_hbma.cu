@@ -290,58 +290,54 @@ __device__ __forceinline__ void tile_level(const uint8_t* smem, const HbmaParams
     atomicAdd(p.counters + 1, (unsigned long long)(nx * ny) * B * B);
   }
   constexpr float inv_area = 1.0f / (float)(B * B);
-  if constexpr (TOP && G <= 3) {
-    const uint32_t xmask = __ballot_sync(0xffffffffu, xok) >> gbase;
-    uint32_t best_s = 0xffffffffu;
-    int best_i = 0;
-    bool all_upd = true;
-#pragma unroll
-    for (int dy = 0; dy < G; ++dy) {
-      const int y = cy - R + dy;
-      const bool yok = (y >= 0) && (y <= fh - B);
-#pragma unroll
-      for (int dj = 0; dj < G; ++dj) {
-        const uint32_t s = __shfl_sync(0xffffffffu, acc[dy], gbase + dj);
-        if (yok && ((xmask >> dj) & 1u)) {
-          if (s <= best_s) { best_s = s; best_i = dy * G + dj; }
-          else all_upd = false;
-        }
-      }
-    }
-    cur = (float)best_s * inv_area;
-    mx = all_upd ? 0 : (best_i % G) - R;
-    my = all_upd ? 0 : (best_i / G) - R;
-  } else if constexpr (TOP) {
-    // The same scan (libs/motion.cpp:312-337) without replaying G*G candidates in every lane:
+  if constexpr (TOP) {
+    // The scan of libs/motion.cpp:312-337 without replaying G*G candidates in every lane:
     //   * "<=" => the LAST minimum in raster order wins: packed (sad << 8 | 255 - index) minimum;
-    //   * every candidate updated the minimum <=> the SADs never increase along the raster order
-    //     of the clamped window: neighbouring columns within a row (one shuffle per row) and the
-    //     last valid column of a row against the first valid column of the next row.
+    //   * every candidate updated the minimum <=> the SADs never increase along the raster order of
+    //     the clamped window.  A sequence that never increases has no later element above ANY earlier
+    //     one, so a lane first tests its own column (a later row above an earlier row): on textured
+    //     content that settles nearly every block with G - 1 compares and one ballot.  Only if some
+    //     block of the warp is left open do the lanes compare neighbouring columns within a row (one
+    //     shuffle per row) and the last valid column of a row against the first valid column of the
+    //     next row (two shuffles per row).
     constexpr uint32_t GM = (1u << G) - 1u;
     const uint32_t xmask = (__ballot_sync(0xffffffffu, xok) >> gbase) & GM;
-    const int c0 = __ffs((int)xmask) - 1, c1 = 31 - __clz((int)xmask);  // valid columns: c0..c1 (contiguous)
-    const bool right_ok = xok && dxi + 1 < G && ((xmask >> (dxi + 1)) & 1u);
     uint32_t key = 0xffffffffu;
-    bool viol = false;
-    bool prev_row_ok = false;
-    uint32_t prev_last = 0;
+    bool viol = false, prev_ok = false;
+    uint32_t prev = 0;
 #pragma unroll
     for (int dy = 0; dy < G; ++dy) {
       const int y = cy - R + dy;
-      const bool yok = (y >= 0) && (y <= fh - B);
-      if (xok && yok) key = min(key, (acc[dy] << 8) | (uint32_t)(255 - (dy * G + dxi)));
-      const uint32_t right = __shfl_down_sync(0xffffffffu, acc[dy], 1);
-      viol |= yok && right_ok && right > acc[dy];
-      const uint32_t first = __shfl_sync(0xffffffffu, acc[dy], gbase + max(c0, 0));
-      const uint32_t last = __shfl_sync(0xffffffffu, acc[dy], gbase + max(c1, 0));
-      viol |= yok && prev_row_ok && first > prev_last;
-      prev_row_ok = yok;
-      prev_last = last;
+      const bool ok = xok && (y >= 0) && (y <= fh - B);
+      if (ok) key = min(key, (acc[dy] << 8) | (uint32_t)(255 - (dy * G + dxi)));
+      viol |= ok && prev_ok && acc[dy] > prev;
+      if (ok) { prev = acc[dy]; prev_ok = true; }
+    }
+    uint32_t vb = __ballot_sync(0xffffffffu, viol);
+    const bool real = (int)((threadIdx.x & 31) / G) < Gm::BPW;  // (lanes past the last block of the warp idle)
+    if (__any_sync(0xffffffffu, real && ((vb >> gbase) & GM) == 0u)) {
+      const int c0 = __ffs((int)xmask) - 1, c1 = 31 - __clz((int)xmask);  // valid columns: c0..c1 (contiguous)
+      const bool right_ok = xok && dxi + 1 < G && ((xmask >> (dxi + 1)) & 1u);
+      bool prev_row_ok = false;
+      uint32_t prev_last = 0;
+#pragma unroll
+      for (int dy = 0; dy < G; ++dy) {
+        const int y = cy - R + dy;
+        const bool yok = (y >= 0) && (y <= fh - B);
+        const uint32_t right = __shfl_down_sync(0xffffffffu, acc[dy], 1);
+        viol |= yok && right_ok && right > acc[dy];
+        const uint32_t first = __shfl_sync(0xffffffffu, acc[dy], gbase + max(c0, 0));
+        const uint32_t last = __shfl_sync(0xffffffffu, acc[dy], gbase + max(c1, 0));
+        viol |= yok && prev_row_ok && first > prev_last;
+        prev_row_ok = yok;
+        prev_last = last;
+      }
+      vb = __ballot_sync(0xffffffffu, viol);
     }
     uint32_t best = 0xffffffffu;
 #pragma unroll
     for (int dj = 0; dj < G; ++dj) best = min(best, __shfl_sync(0xffffffffu, key, gbase + dj));
-    const bool all_upd = ((__ballot_sync(0xffffffffu, viol) >> gbase) & GM) == 0u;
+    const bool all_upd = ((vb >> gbase) & GM) == 0u;
     const int best_i = 255 - (int)(best & 0xffu);
     cur = (float)(best >> 8) * inv_area;
     mx = all_upd ? 0 : (best_i % G) - R;
