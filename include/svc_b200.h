@@ -170,6 +170,7 @@ typedef struct svc_session_config {
 #define SVC_HBMA_FAMILY_GENERIC 1u /* hbma_generic_kernel: any block shape / level count / range */
 #define SVC_HBMA_FAMILY_POOL 2u    /* single-launch pooled kernel (16x16 blocks, r = 5..64) */
 #define SVC_HBMA_FAMILY_WINDOW 3u  /* per-block TMA window kernels (16x16 blocks) */
+#define SVC_HBMA_FAMILY_TILE 4u    /* bounded-reach tile kernel also where the strip kernel would be picked */
 
 typedef struct svc_session_info {
   uint32_t padded_w, padded_h;       /* libs/encoder.cpp:166-169 */

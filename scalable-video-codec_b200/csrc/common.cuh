@@ -54,7 +54,7 @@ cudaError_t launch_pyr_levels(uint8_t* d_pyr, const PyrLayout& lay, uint32_t fir
 
 // ---- K2: hierarchical block matching ---------------------------------------
 // svc_session_config.hbma_kernel_family (include/svc_b200.h: SVC_HBMA_FAMILY_*)
-enum : uint32_t { kHbmaAuto = 0, kHbmaGeneric = 1, kHbmaPool = 2, kHbmaWindow = 3 };
+enum : uint32_t { kHbmaAuto = 0, kHbmaGeneric = 1, kHbmaPool = 2, kHbmaWindow = 3, kHbmaTile = 4 };
 struct HbmaParams {
   const uint8_t* pyr;  // slot array; frame i: tracked = slot i, anchor = slot i+1
   PyrLayout lay;

@@ -57,6 +57,10 @@ struct HbmaParams;
 bool rs_level_supported(const HbmaParams& p);
 cudaError_t launch_rs_level(const HbmaParams& p, uint32_t lvl, bool top, cudaStream_t st);
 
+// the encoder default (16x16 blocks, 4 levels, r = 1): strip-per-lane tile kernel (k_hbma_strip.cu)
+bool strip_supported(const HbmaParams& p);
+cudaError_t launch_strip(const HbmaParams& p, cudaStream_t st);
+
 // large-range 16x16 search with pooled work items and pre-shifted window copies (k_hbma_pool.cu);
 // returns false when the configuration is outside its limits (the caller picks another kernel)
 // (*extra_launches += launches beyond the first, for the level-synchronous path)

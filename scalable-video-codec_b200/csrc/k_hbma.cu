@@ -786,6 +786,10 @@ static bool try_launch_tile(const HbmaParams& p, cudaStream_t st, cudaError_t* e
     return false;
   }
   if (p.bw != 16 || p.bh != 16) return false;
+  if (p.family == kHbmaAuto && strip_supported(p)) {  // the encoder default: k_hbma_strip.cu
+    *err = launch_strip(p, st);
+    return true;
+  }
 #define SVC_TILE_CASE(LL, RR) \
   if (L == LL && r == RR) { *err = launch_tile<LL, RR>(p, st); return true; }
   SVC_TILE_CASE(4, 1) SVC_TILE_CASE(4, 2) SVC_TILE_CASE(4, 3) SVC_TILE_CASE(4, 4)
@@ -869,7 +873,7 @@ cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches) {
   if (p.family != kHbmaGeneric) {
     cudaError_t e = cudaSuccess;
     const bool any = p.family == kHbmaAuto;
-    if ((any && try_launch_tile(p, st, &e)) ||
+    if (((any || p.family == kHbmaTile) && try_launch_tile(p, st, &e)) ||
         ((any || p.family == kHbmaPool) && try_launch_pool(p, st, &e, n_launches)) ||
         ((any || p.family == kHbmaWindow) && try_launch_window(p, st, &e))) {
       if (n_launches) *n_launches += 1;

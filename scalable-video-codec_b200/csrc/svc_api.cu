@@ -839,7 +839,7 @@ int svc_session_create(const svc_session_config* cfg_in, svc_session** out) {
   memcpy(&cfg_copy, cfg_in, cfg_in->struct_size);
   cfg_copy.struct_size = sizeof(svc_session_config);
   const svc_session_config* cfg = &cfg_copy;
-  if (cfg->hbma_kernel_family > SVC_HBMA_FAMILY_WINDOW)
+  if (cfg->hbma_kernel_family > SVC_HBMA_FAMILY_TILE)
     return fail(SVC_ERR_INVALID_ARG, "hbma_kernel_family must be one of SVC_HBMA_FAMILY_*");
   *out = nullptr;
   // Validate(EncoderConfig), libs/encoder.cpp:62-142 (hot-path fields)

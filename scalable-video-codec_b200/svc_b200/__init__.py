@@ -13,7 +13,7 @@ from .binding import (  # noqa: F401
     EstimateMotionExhaustiveSearch, y_pyramid, dct_planar, encode_frame_stream,
     patch_block_types, stream_layout, gaze_rect, decode_frame_blocks, decode_frames_device, Session, SessionConfig, PinnedBuffer, DeviceBuffer,
     STAGE_Y_PYRAMID, STAGE_HBMA, STAGE_DCT_STREAM, STAGE_PYR_DOWN,
-    HBMA_FAMILY_AUTO, HBMA_FAMILY_GENERIC, HBMA_FAMILY_POOL, HBMA_FAMILY_WINDOW,
+    HBMA_FAMILY_AUTO, HBMA_FAMILY_GENERIC, HBMA_FAMILY_POOL, HBMA_FAMILY_WINDOW, HBMA_FAMILY_TILE,
 )
 from .shard import shard_frame_ranges, gather_streams  # noqa: F401
 from .synth import SyntheticSequence  # noqa: F401

@@ -19,7 +19,7 @@ _u32p = C.POINTER(C.c_uint32)
 
 STAGE_Y_PYRAMID, STAGE_HBMA, STAGE_DCT_STREAM, STAGE_PYR_DOWN = 1, 2, 3, 4
 # svc_session_config.hbma_kernel_family (test hook): SVC_HBMA_FAMILY_*
-HBMA_FAMILY_AUTO, HBMA_FAMILY_GENERIC, HBMA_FAMILY_POOL, HBMA_FAMILY_WINDOW = 0, 1, 2, 3
+HBMA_FAMILY_AUTO, HBMA_FAMILY_GENERIC, HBMA_FAMILY_POOL, HBMA_FAMILY_WINDOW, HBMA_FAMILY_TILE = 0, 1, 2, 3, 4
 
 
 class SvcError(RuntimeError):

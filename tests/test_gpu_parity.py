@@ -208,7 +208,7 @@ def test_hbma_pooled_window_path_vs_oracle(gpu, oracle, L, R, w, h):
     assert np.array_equal(mv[0], emv) and np.array_equal(mad[0], emad)
 
 
-@pytest.mark.parametrize("family", ["GENERIC", "WINDOW"])
+@pytest.mark.parametrize("family", ["GENERIC", "WINDOW", "TILE"])
 @pytest.mark.parametrize("L,R", [(1, 8), (2, 16), (4, 8), (4, 64), (5, 64)])
 def test_hbma_kernel_family_hook_vs_oracle(gpu, oracle, family, L, R):
     """svc_session_config.hbma_kernel_family (the library's one test hook): the universal kernel and
@@ -224,6 +224,43 @@ def test_hbma_kernel_family_hook_vs_oracle(gpu, oracle, family, L, R):
     for i in (1, 2):
         emv, emad = oracle.hbma(pyr[i - 1], pyr[i], R)
         assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad)
+
+
+@pytest.mark.parametrize("w,h,n", [(1920, 1080, 3), (960, 540, 3), (130, 70, 4), (16, 16, 3), (24, 200, 3), (400, 24, 3),
+                                   (272, 144, 5), (128, 128, 3), (144, 272, 3)])
+def test_hbma_strip_kernel_default_config(gpu, oracle, w, h, n):
+    """Encoder default (16x16, R=8, L=4): hbma_strip_kernel (k_hbma_strip.cu: a lane owns a strip of a
+    block and all nine candidates) against the oracle and against the bounded-reach tile kernel it
+    replaced (test hook family TILE) -- whole tiles, partial tiles on both edges, motion fields of one
+    block row / column, a single block."""
+    frames = SyntheticSequence(w, h, n, seed=w + h).frames()
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h)) as s:
+        mv, mad, _ = s.encode(frames, want_stream=False)
+        pw, ph = s.padded_w, s.padded_h
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, hbma_kernel_family=gpu.HBMA_FAMILY_TILE)) as s:
+        mv_t, mad_t, _ = s.encode(frames, want_stream=False)
+    assert np.array_equal(mv, mv_t) and np.array_equal(mad, mad_t)
+    pyr = [oracle.y_pyramid(f, pw, ph, 4) for f in frames]
+    for i in range(1, n):
+        emv, emad = oracle.hbma(pyr[i - 1], pyr[i], 8)
+        assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad)
+
+
+def test_hbma_strip_kernel_special_content(gpu, oracle):
+    """Flat, saturated and ramp frames through the strip kernel: ties everywhere (first minimum at the
+    refinement levels, last minimum and the zero-vector rule at the top level)."""
+    w, h = 208, 144
+    ramp = (np.arange(w, dtype=np.int64)[None, :, None] * 3 + np.arange(h)[:, None, None] * 5 + np.zeros((1, 1, 3), np.int64))
+    seqs = [np.stack([np.full((h, w, 3), v, np.uint8) for v in (0, 255, 255, 17)]),
+            np.stack([(ramp % 256).astype(np.uint8), ((ramp + 7) % 256).astype(np.uint8), ((ramp // 2) % 256).astype(np.uint8)])]
+    for frames in seqs:
+        with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h)) as s:
+            mv, mad, _ = s.encode(frames, want_stream=False)
+            pw, ph = s.padded_w, s.padded_h
+        pyr = [oracle.y_pyramid(f, pw, ph, 4) for f in frames]
+        for i in range(1, len(frames)):
+            emv, emad = oracle.hbma(pyr[i - 1], pyr[i], 8)
+            assert np.array_equal(mv[i - 1], emv) and np.array_equal(mad[i - 1], emad)
 
 
 @pytest.mark.parametrize("L,R", [(2, 10), (2, 16), (2, 27), (2, 32), (2, 50), (2, 64), (3, 20), (3, 32), (3, 45),
