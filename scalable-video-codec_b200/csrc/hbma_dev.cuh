@@ -59,7 +59,7 @@ cudaError_t launch_rs_level(const HbmaParams& p, uint32_t lvl, bool top, cudaStr
 
 // the encoder default (16x16 blocks, 4 levels, r = 1): strip-per-lane tile kernel (k_hbma_strip.cu)
 bool strip_supported(const HbmaParams& p);
-cudaError_t launch_strip(const HbmaParams& p, cudaStream_t st);
+cudaError_t launch_strip(const HbmaParams& p, cudaStream_t st, int* extra_launches);
 
 // large-range 16x16 search with pooled work items and pre-shifted window copies (k_hbma_pool.cu);
 // returns false when the configuration is outside its limits (the caller picks another kernel)

@@ -773,7 +773,7 @@ cudaError_t launch_tile_upper3(const HbmaParams& p, cudaStream_t st) {
 }
 
 // (levels, r) pairs with a tiled instantiation; everything else takes the generic kernel
-static bool try_launch_tile(const HbmaParams& p, cudaStream_t st, cudaError_t* err) {
+static bool try_launch_tile(const HbmaParams& p, cudaStream_t st, cudaError_t* err, int* extra_launches) {
   if (p.n_frames > 65535 || (p.mvh + 3) / 4 > 65535) return false;
   const uint32_t L = p.lay.levels, r = p.r;
   if (p.bw == 8 && p.bh == 8) {  // 8x8 motion blocks: the same kernel, base block 8
@@ -787,7 +787,7 @@ static bool try_launch_tile(const HbmaParams& p, cudaStream_t st, cudaError_t* e
   }
   if (p.bw != 16 || p.bh != 16) return false;
   if (p.family == kHbmaAuto && strip_supported(p)) {  // the encoder default: k_hbma_strip.cu
-    *err = launch_strip(p, st);
+    *err = launch_strip(p, st, extra_launches);
     return true;
   }
 #define SVC_TILE_CASE(LL, RR) \
@@ -873,7 +873,7 @@ cudaError_t launch_hbma(const HbmaParams& p, cudaStream_t st, int* n_launches) {
   if (p.family != kHbmaGeneric) {
     cudaError_t e = cudaSuccess;
     const bool any = p.family == kHbmaAuto;
-    if (((any || p.family == kHbmaTile) && try_launch_tile(p, st, &e)) ||
+    if (((any || p.family == kHbmaTile) && try_launch_tile(p, st, &e, n_launches)) ||
         ((any || p.family == kHbmaPool) && try_launch_pool(p, st, &e, n_launches)) ||
         ((any || p.family == kHbmaWindow) && try_launch_window(p, st, &e))) {
       if (n_launches) *n_launches += 1;

@@ -47,7 +47,7 @@ def main():
         outs[name] = (mv.cpu().numpy().copy(), mad.cpu().numpy().copy())
         res[name] = []
     for _ in range(a.reps):
-        for name in ("strip", "tile"):
+        for name in sess:
             s, mv, mad = sess[name]
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(ts)
