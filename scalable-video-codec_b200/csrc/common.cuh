@@ -8,6 +8,34 @@ namespace svc {
 constexpr int kMaxLevels = 8;
 constexpr int kNumSms = 148;  // B200
 
+// ---- programmatic dependent launch (the motion stream's chain hand-over -> pyramid -> search) ------
+// A kernel launched with launch_dependent() may be scheduled while the tail of its predecessor in
+// the stream still runs; it must call grid_dependency_wait() before it reads anything the
+// predecessor wrote and before its first global write (the predecessor's results are complete and
+// visible after it).  grid_dependency_release() lets the NEXT kernel of the chain be scheduled early; it
+// is called right AFTER the wait, so that a kernel never starts before the predecessor of its
+// predecessor has completed.  Both are no-ops for a kernel launched the ordinary way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 // Device layout of one Y pyramid "slot" (one frame): levels are stored one
 // after another, each with a 128-byte-multiple row pitch (TMA needs 16-byte
 // strides; the reference keeps tightly packed Mats, libs/encoder.cpp:197-219,

@@ -51,7 +51,6 @@ struct HbmaStripMaps {
 namespace {
 
 constexpr int kSTB = 8;  // tile edge in motion blocks
-constexpr uint32_t kStripResident = kNumSms * 5;  // CTAs in flight (5 per SM: shared memory)
 
 __host__ __device__ constexpr int sg_align(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -67,7 +66,6 @@ struct StripGeom {
     for (int i = 0; i < l; ++i) o += sg_align(tw(i) * th(i) + 16, 128);
     return o;
   }
-  __host__ __device__ static constexpr int smem_bytes() { return off(kSL); }
 };
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar_addr) {
@@ -322,6 +320,8 @@ hbma_strip_coarse_kernel(const __grid_constant__ HbmaStripMaps maps, const HbmaP
   const int tile_bx0 = blockIdx.x * kSTB, tile_by0 = blockIdx.y * kSTB;
   const int f = blockIdx.z;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[0]);
+  grid_dependency_wait();  // the pyramid levels of this batch (launch_pyr_levels) are complete
+  grid_dependency_release();
   if (threadIdx.x == 0) issue_windows(maps, smem, bar0, 2, 3, tile_bx0, tile_by0, f);
   const PipeConsts pc = {p.lay.levels << 6, p.lay.levels << 14, p.lay.levels << 22};
   const int cb = threadIdx.x;
@@ -364,6 +364,8 @@ hbma_strip_fine_kernel(const __grid_constant__ HbmaStripMaps maps, const HbmaPar
   const int tile_bx0 = blockIdx.x * kSTB, tile_by0 = blockIdx.y * kSTB;
   const int f = blockIdx.z;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[0]);
+  grid_dependency_wait();  // level-2 vectors and MADs of the coarse kernel are complete
+  grid_dependency_release();
   if (threadIdx.x == 0) issue_windows(maps, smem, bar0, 0, 1, tile_bx0, tile_by0, f);
   const PipeConsts pc = {p.lay.levels << 6, p.lay.levels << 14, p.lay.levels << 22};
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -422,12 +424,12 @@ cudaError_t launch_strip(const HbmaParams& p, cudaStream_t st, int* extra_launch
   }
   constexpr int kFineSmem = Gm::off(2), kCoarseSmem = Gm::off(kSL) - Gm::off(2);
   dim3 grid((p.mvw + kSTB - 1) / kSTB, (p.mvh + kSTB - 1) / kSTB, p.n_frames);
-  hbma_strip_coarse_kernel<<<grid, 64, kCoarseSmem, st>>>(maps, p);
   cudaError_t e = cudaFuncSetAttribute(hbma_strip_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFineSmem);
   if (e != cudaSuccess) return e;
-  hbma_strip_fine_kernel<<<grid, 128, kFineSmem, st>>>(maps, p);
+  e = launch_dependent(hbma_strip_coarse_kernel, grid, dim3(64), kCoarseSmem, st, maps, p);
+  if (e != cudaSuccess) return e;
   if (extra_launches) *extra_launches += 1;
-  return cudaGetLastError();
+  return launch_dependent(hbma_strip_fine_kernel, grid, dim3(128), kFineSmem, st, maps, p);
 }
 
 }  // namespace svc

@@ -222,6 +222,8 @@ pyr_down_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restrict
   constexpr int kSrcH = 2 * kTileH + 3;
   __shared__ __align__(128) uint8_t tile[kSrcH * kPdSrcW];
   __shared__ __align__(8) uint64_t bar;
+  grid_dependency_wait();
+  grid_dependency_release();
   uint8_t* slot = pyr + (uint64_t)(first_slot + blockIdx.z) * slot_bytes;
   const int x0t = blockIdx.x * kPdTileW, y0t = blockIdx.y * kTileH;
   const int sx0 = 2 * x0t - 16, sy0 = 2 * y0t - 2;  // source coords of tile[0][0] (16-byte aligned)
@@ -321,6 +323,8 @@ pyr_down2_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restric
   __shared__ __align__(128) uint8_t tile[kF0Rows * kF0BoxW];
   __shared__ __align__(16) uint8_t t1[(kF1Rpt * kF1Strips + 1) * kF1Pitch];
   __shared__ __align__(8) uint64_t bar;
+  grid_dependency_wait();
+  grid_dependency_release();
   uint8_t* slot = pyr + (uint64_t)(first_slot + blockIdx.z) * slot_bytes;
   const int x0 = blockIdx.x * kF2TileW, y0 = blockIdx.y * kF2TileH;  // level l+2 tile origin
   const int u0 = 2 * x0 - 2, v0 = 2 * y0 - 2;                        // level l+1 coords of region (0, 0)
@@ -470,6 +474,8 @@ pyr_down_small_kernel(uint8_t* __restrict__ pyr, uint64_t slot_bytes, uint32_t f
 // cudaMemcpyAsync D2D may be queued on the copy engine that is busy with a 400 MB device-to-host
 // transfer of the host path, which would stall the whole motion stream behind it.
 __global__ void __launch_bounds__(256) copy_slot_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n) {
+  grid_dependency_wait();
+  grid_dependency_release();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = src[i];
 }
@@ -532,13 +538,11 @@ cudaError_t launch_pyr_down(uint8_t* d_pyr, const PyrLayout& lay,
   cudaError_t e = encode_level_map(&map, d_pyr, lay, l, first_slot + n_frames, kPdSrcW, 2 * tile_h + 3);
   if (e != cudaSuccess) return e;
   dim3 grid((dw + kPdTileW - 1) / kPdTileW, (dh + tile_h - 1) / tile_h, n_frames);
-#define SVC_PYR_LAUNCH(RPT)                                                                        \
-  pyr_down_kernel<RPT><<<grid, block, 0, st>>>(map, d_pyr, lay.slot_bytes, first_slot, lay.w[l],   \
-                                               lay.h[l], lay.off[l + 1], dw, dh, lay.pitch[l + 1])
-  if (rpt == 8) SVC_PYR_LAUNCH(8);
-  else SVC_PYR_LAUNCH(2);
+#define SVC_PYR_LAUNCH(RPT)                                                                             \
+  launch_dependent(pyr_down_kernel<RPT>, grid, block, 0, st, map, d_pyr, lay.slot_bytes, first_slot, lay.w[l], \
+                   lay.h[l], lay.off[l + 1], dw, dh, lay.pitch[l + 1])
+  return rpt == 8 ? SVC_PYR_LAUNCH(8) : SVC_PYR_LAUNCH(2);
 #undef SVC_PYR_LAUNCH
-  return cudaGetLastError();
 }
 
 // levels src_level+1 and src_level+2 in one launch (pyr_down2_kernel)
@@ -549,10 +553,9 @@ static cudaError_t launch_pyr_down2(uint8_t* d_pyr, const PyrLayout& lay, uint32
   cudaError_t e = encode_level_map(&map, d_pyr, lay, l, first_slot + n_frames, kF0BoxW, kF0BoxH);
   if (e != cudaSuccess) return e;
   dim3 grid((lay.w[l + 2] + kF2TileW - 1) / kF2TileW, (lay.h[l + 2] + kF2TileH - 1) / kF2TileH, n_frames);
-  pyr_down2_kernel<<<grid, kFusedThreads, 0, st>>>(map, d_pyr, lay.slot_bytes, first_slot, lay.w[l], lay.h[l],
-                                                   lay.off[l + 1], lay.w[l + 1], lay.h[l + 1], lay.pitch[l + 1],
-                                                   lay.off[l + 2], lay.w[l + 2], lay.h[l + 2], lay.pitch[l + 2]);
-  return cudaGetLastError();
+  return launch_dependent(pyr_down2_kernel, grid, dim3(kFusedThreads), 0, st, map, d_pyr, lay.slot_bytes, first_slot,
+                          lay.w[l], lay.h[l], lay.off[l + 1], lay.w[l + 1], lay.h[l + 1], lay.pitch[l + 1],
+                          lay.off[l + 2], lay.w[l + 2], lay.h[l + 2], lay.pitch[l + 2]);
 }
 
 // All levels 1 .. L-1 of slots first_slot .. first_slot+n_frames-1 from their level 0: level 0 -> 1
