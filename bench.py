@@ -405,8 +405,9 @@ def run_ours(a):
 
     d_in = torch.empty(F * fin, dtype=torch.uint8, device="cuda")
     d_st = torch.empty(F * fst, dtype=torch.uint8, device="cuda")  # (F, not n_enc: the stage timings run whole batches)
-    d_mv = torch.empty(n_enc * mvn * 2, dtype=torch.float32, device="cuda")
-    d_mad = torch.empty(n_enc * mvn, dtype=torch.float32, device="cuda")
+    # (F fields, not n_enc: the stage timings search whole batches of F // batch * batch pairs, slot 0 included)
+    d_mv = torch.empty(F * mvn * 2, dtype=torch.float32, device="cuda")
+    d_mad = torch.empty(F * mvn, dtype=torch.float32, device="cuda")
     svc.binding._check(svc.lib().svc_memcpy_h2d(local, d_in.data_ptr(), h_in.ptr, F * fin))
     torch.cuda.synchronize()
 
@@ -445,8 +446,8 @@ def run_ours(a):
         ne_ = n_enc
         picks_ = sorted({int(round(x)) - 1 for x in np.linspace(1, ne_, min(8, ne_))})
         st_dev = {k: d_st[k * fst:(k + 1) * fst].cpu().numpy() for k in picks_}
-        par_out["device_resident"] = (d_mv.cpu().numpy().reshape(ne_, mh_, mw_, 2),
-                                      d_mad.cpu().numpy().reshape(ne_, mh_, mw_), st_dev.__getitem__)
+        par_out["device_resident"] = (d_mv[:ne_ * mvn * 2].cpu().numpy().reshape(ne_, mh_, mw_, 2),
+                                      d_mad[:ne_ * mvn].cpu().numpy().reshape(ne_, mh_, mw_), st_dev.__getitem__)
 
     # ---------------- per-stage timing (dominant kernel roofline) -------------------
     def time_stage(fn, name, reps=40):
@@ -513,7 +514,9 @@ def run_ours(a):
             pass
         kernels = {"dct_stream_y": "dct8x8_stream_kernel<withY> (K3: block DCT + stream records + level-0 luma)",
                    "pyr_down": "pyr_down kernels (K1b: pyramid levels 1..L-1 of the batch)",
-                   "hbma": "hbma_tile_kernel<4,1,16> (K2: 4-level search, r = 1; HBM-bound at this range, SURVEY 8d)"}
+                   "hbma": ("hbma_strip_coarse_kernel + hbma_strip_fine_kernel (K2: 4-level search, r = 1; against the HBM "
+                            "roofline at this range, SURVEY 8d)") if (a.levels, a.search_range) == (4, 8) else
+                           f"K2 search kernels the dispatcher picks for L={a.levels}, R={a.search_range}"}
         rooflines = {}
         for k, st_ in stages.items():
             rooflines[k] = {"kernel": kernels[k], "bound": "hbm", "achieved": st_["gbs"], "peak": hbm_peak,
