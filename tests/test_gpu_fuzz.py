@@ -119,3 +119,39 @@ def test_session_fused_square_transform_blocks(gpu, oracle, w, h, mb, L, tb, n, 
             e = exp.view(np.uint32).reshape(-1, rec)
             assert np.array_equal(g[:, 0], e[:, 0]), i
             assert np.abs(g[:, 1:].view(np.float32) - e[:, 1:].view(np.float32)).max() <= DCT_TOL, i
+
+
+def _default_cfgs(n, seed):
+    rng = np.random.default_rng(seed)
+    return [(int(rng.integers(16, 420)), int(rng.integers(16, 300)), int(rng.integers(0, 4)), int(rng.integers(1, 1 << 30)))
+            for _ in range(n)]
+
+
+@pytest.mark.parametrize("cfg", _default_cfgs(24, 77))
+def test_random_default_config_strip_kernels(gpu, oracle, cfg):
+    """Encoder default (16x16, R=8, L=4: hbma_strip_coarse/fine_kernel) on random frame sizes and four
+    kinds of content: the synthetic sequence with pans up to the full reach of the search (15 pixels at
+    level 0), unrelated frames (vectors all over the bounded window), white noise, and frames that differ
+    by a constant (every candidate ties somewhere).  Against the oracle and the tile kernel."""
+    w, h, kind, seed = cfg
+    rng = np.random.default_rng(seed)
+    if kind == 0:
+        frames = SyntheticSequence(w, h, 4, seed=seed % 9973, n_rects=3, max_pan=15).frames()
+    elif kind == 1:
+        frames = np.stack([SyntheticSequence(w, h, 1, seed=seed % 9973 + k).frame(0) for k in range(3)])
+    elif kind == 2:
+        frames = rng.integers(0, 256, size=(3, h, w, 3), dtype=np.uint8)
+    else:
+        base = SyntheticSequence(w, h, 1, seed=seed % 9973).frame(0).astype(np.int32)
+        frames = np.stack([np.clip(base + d, 0, 255).astype(np.uint8) for d in (0, 9, -7)])
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, max_batch=2)) as s:
+        mv, mad, _ = s.encode(frames, want_stream=False)
+        pw, ph = s.padded_w, s.padded_h
+    with gpu.Session(gpu.SessionConfig(frame_w=w, frame_h=h, hbma_kernel_family=gpu.HBMA_FAMILY_TILE)) as s:
+        mv_t, mad_t, _ = s.encode(frames, want_stream=False)
+    assert np.array_equal(mv, mv_t) and np.array_equal(mad, mad_t), cfg
+    pyr = [oracle.y_pyramid(f, pw, ph, 4) for f in frames]
+    for i in range(1, len(frames)):
+        emv, emad = oracle.hbma(pyr[i - 1], pyr[i], 8)
+        assert np.array_equal(mv[i - 1], emv), (cfg, i)
+        assert np.array_equal(mad[i - 1], emad), (cfg, i)
