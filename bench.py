@@ -362,8 +362,20 @@ def run_ours(a):
     numa = bind_to_gpu_numa_node(local)  # before any pinned allocation (first-touch placement)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner to stdout when the first communicator is created: keep stdout to
+        # the one JSON line by pointing fd 1 at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     svc.lib()
 
     def barrier():
