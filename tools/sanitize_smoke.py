@@ -23,10 +23,10 @@ def main():
     ok = True
     w, h, n = 208, 112, 3
     frames = svc.SyntheticSequence(w, h, n, seed=11).frames()
-    # (levels, range): default tile kernel, rs kernels at r = 8 / 16 / 4 (hybrid), shared-window / pooled /
+    # (levels, range): default strip kernels (and the tile kernel they replaced, through the hook), rs kernels at r = 8 / 16 / 4 (hybrid), shared-window / pooled /
     # striped kernels, the generic kernel through the test hook
     for L, R, fam in ((4, 8, 0), (2, 16, 0), (4, 64, 0), (2, 32, 0), (1, 8, 0), (5, 64, 0), (1, 16, 0), (2, 64, 0),
-                      (1, 40, 0), (3, 8, 0), (4, 8, svc.HBMA_FAMILY_GENERIC), (2, 16, svc.HBMA_FAMILY_POOL),
+                      (1, 40, 0), (3, 8, 0), (4, 8, svc.HBMA_FAMILY_GENERIC), (4, 8, svc.HBMA_FAMILY_TILE), (2, 16, svc.HBMA_FAMILY_POOL),
                       (2, 16, svc.HBMA_FAMILY_WINDOW)):
         with svc.Session(svc.SessionConfig(frame_w=w, frame_h=h, mv_search_range=R, pyr_lvl_count=L,
                                            hbma_kernel_family=fam, max_batch=2)) as s:
