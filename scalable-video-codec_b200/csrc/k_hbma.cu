@@ -147,8 +147,11 @@ hbma_generic_kernel(HbmaParams p) {
 
 
 // ---------------------------------------------------------------------------
-// Tiled fast path (16x16 blocks, small top-level range: the encoder default
-// R=8/L=4 -> r=1, and the low-r corner of the range sweep).
+// Tiled fast path (16x16 or 8x8 blocks, small top-level range r <= 4: the low-r
+// corner of the range sweep, 8x8 motion blocks, the three coarsest levels of the
+// 5-level hybrid).  The encoder default (16x16, R=8/L=4 -> r=1) ran here in
+// round 1 and now runs on the strip kernels of k_hbma_strip.cu; the test hook
+// family kHbmaTile still routes it here.
 //
 // A CTA owns a tile of TBX x 4 motion blocks.  Because the reach of the search
 // at level l is bounded by d_l = r (2^(L-l) - 1), the whole reference-frame
