@@ -1062,8 +1062,13 @@ int svc_session_encode(svc_session* s, const uint8_t* frames, uint32_t n_frames,
     const int b = chunk & 1;
     const uint32_t bi = chunk % s->in_ring;
     // PCIe-bound: small chunks keep H2D | kernels | D2H overlapped and the exposed head
-    // and tail of the pipeline short
-    const uint32_t m = std::min(std::min(s->info.max_batch, s->host_chunk), n_frames - done_in);
+    // and tail of the pipeline short.  The record download (25 MB per 1080p frame) is the critical
+    // path and cannot start before the first chunk is uploaded and encoded, so the first chunks ramp up
+    // (base/8, base/4, base/2, base frames): the download of chunk c (4x the bytes of an upload per
+    // frame) still covers the upload of the twice larger chunk c+1.
+    const uint32_t base = std::min(s->info.max_batch, s->host_chunk);
+    const uint32_t ramp = chunk < 3 ? std::max(2u, base >> (3 - chunk)) : base;
+    const uint32_t m = std::min(std::min(base, ramp), n_frames - done_in);
     const uint32_t ne = s->have_prev ? m : m - 1;
     if (chunk >= s->in_ring) CU(cudaStreamWaitEvent(s->s_in, s->ev_used[bi], 0));  // d_in[bi] consumed
     if (chunk >= 2) CU(cudaStreamWaitEvent(s->stream, s->ev_out[b], 0));           // outputs[b] drained
