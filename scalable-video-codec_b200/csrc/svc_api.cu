@@ -620,14 +620,14 @@ struct svc_session {
   float* d_scratch = nullptr;  // generic DCT path only
   uint32_t scratch_frames = 0;
   // host path staging (double buffered), allocated on first use
-  static constexpr int kInRing = 8;  // input staging slots: the upload runs up to 8 chunks ahead of the kernels
+  static constexpr int kInRing = 8;  // input staging slots: the upload runs up to 8 chunks ahead of the kernels (24 measured: no gain)
   uint8_t* d_in[kInRing] = {};
   cudaEvent_t ev_in_ring[kInRing] = {}, ev_used[kInRing] = {};
   uint32_t in_ring = 2;
   float* d_mv[2] = {nullptr, nullptr};
   float* d_mad[2] = {nullptr, nullptr};
   uint8_t* d_st[2] = {nullptr, nullptr};
-  uint32_t* d_bt[8] = {};  // (one per input slot)
+  uint32_t* d_bt[kInRing] = {};  // (one per input slot)
   cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
   bool staging = false;
   uint32_t host_chunk = 16;  // frames per pipeline stage of svc_session_encode
