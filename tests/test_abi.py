@@ -149,3 +149,19 @@ def test_stream_layout_reports_the_reference_encoder_decoder_mismatch(svc):
         assert svc.stream_layout(svc.write_header(30, w, h, pw, ph))["consistent"] == 1
     with pytest.raises(svc.SvcError):
         svc.stream_layout(np.zeros(32, np.uint8))
+
+
+def test_header_constants_match_the_binding(svc):
+    """Every SVC_HBMA_FAMILY_* / SVC_STAGE_* value of include/svc_b200.h is the value the ctypes binding
+    uses (the test hook that routes the default configuration to the tile or the strip kernels
+    depends on it), and the session rejects a family beyond the last one defined."""
+    src = open(os.path.join(ROOT, "include", "svc_b200.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(SVC_(?:HBMA_FAMILY|STAGE)_[A-Z0-9_]+)\s+(\d+)u?", src)}
+    fam = {k[len("SVC_"):]: v for k, v in defs.items() if k.startswith("SVC_HBMA_FAMILY_")}
+    assert set(fam) >= {"HBMA_FAMILY_AUTO", "HBMA_FAMILY_GENERIC", "HBMA_FAMILY_POOL", "HBMA_FAMILY_WINDOW", "HBMA_FAMILY_TILE"}
+    for name, value in fam.items():
+        assert getattr(svc, name) == value, name
+    assert sorted(fam.values()) == list(range(len(fam)))
+    for name, value in defs.items():
+        if name.startswith("SVC_STAGE_"):
+            assert getattr(svc, name[len("SVC_"):]) == value, name
